@@ -1,0 +1,78 @@
+"""CPU, build-container only: the oracle restatement against the UNMODIFIED reference run live on the
+PyG shim (skipped where /root/reference is absent, e.g. the GPU box -- the committed golden vectors
+cover that case)."""
+import pytest
+import torch
+
+from oracle import hetero_rgcn_ref as R
+from oracle import ref_harness as H
+
+pytestmark = pytest.mark.skipif(not H.available(), reason="/root/reference not present")
+
+
+def test_eval_predict_and_forward_match_reference(pkg):
+    M, T = H.load_reference(H.FakeClock())
+    g = pkg.synth.make_graph("tiny", seed=3)
+    d = H.to_shim_data(g)
+    cfg = H.make_config(dropout=0.2)
+    model = M.build_model(cfg, (d.node_types, d.edge_types), None)
+    model._init_embeddings(d)
+    # non-trivial running stats
+    model.train()
+    with torch.no_grad():
+        model(d)
+    model.eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    counts = {nt: int(g[nt].num_nodes) for nt in g.node_types}
+    ei = g["patient", "has_lab", "lab"].edge_index
+    with torch.no_grad():
+        ref_pred = model.predict_lab_values(d, ei[0], ei[1])
+        ref_x = model(d)
+        ref_enc = model.encode_nodes(d)
+    taps = {}
+    pred = R.predict_lab_values(sd, counts, list(g.edge_types), g.edge_index_dict, ei[0], ei[1], False, taps=taps)
+    torch.testing.assert_close(pred, ref_pred, rtol=2e-5, atol=2e-6)
+    for nt in counts:
+        torch.testing.assert_close(taps["layer1"][nt], ref_x[nt], rtol=2e-5, atol=2e-6)
+        torch.testing.assert_close(taps["encode"][nt], ref_enc[nt], rtol=2e-5, atol=2e-6)
+
+
+def test_ten_training_steps_track_reference(pkg):
+    """Oracle + torch Adam over the reference's optimizer parameter set (N2) follows the reference's
+    Trainer for 10 steps."""
+    clock = H.FakeClock()
+    M, T = H.load_reference(clock)
+    g = pkg.synth.make_graph("tiny", seed=5)
+    d = H.to_shim_data(g)
+    cfg = H.make_config(dropout=0.0, loss="mse")
+    masker = T.EdgeMasker(d, 0.7, 0.15, 0.15, 0.2, 42)
+    model = M.build_model(cfg, (d.node_types, d.edge_types), None)
+    tr = T.Trainer(model, d, masker, cfg, torch.device("cpu"))
+    model._init_embeddings(d)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    counts = {nt: int(g[nt].num_nodes) for nt in g.node_types}
+    ets, eid = list(g.edge_types), g.edge_index_dict
+    ei = g["patient", "has_lab", "lab"].edge_index
+    attr = g["patient", "has_lab", "lab"].edge_attr
+    m_train = R.split_masks(ei.shape[1], 0.7, 0.15, 42)[0]
+    pi, li, tgt = ei[0][m_train], ei[1][m_train], attr[m_train].squeeze(-1)
+    w = R.lab_weights(li, tgt, counts["lab"])
+    keys = R.trainable_keys(sd)
+    params = [sd[k].requires_grad_(True) for k in keys]
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-5)
+    for step in range(10):
+        seed = int(clock.now) + 1
+        ref_loss = tr.train_epoch()
+        sup = R.supervision_mask(int(m_train.sum()), 0.2, seed)
+        opt.zero_grad()
+        work = {k: v for k, v in sd.items()}
+        pred = R.predict_lab_values(work, counts, ets, eid, pi, li, True, p_drop=0.0)
+        loss = R.weighted_loss(pred, tgt, li, w, sup, "mse")
+        loss.backward()
+        for k, p in zip(keys, params):      # N8: parameters without a gradient are skipped by Adam
+            pass
+        opt.step()
+        assert abs(float(loss) - ref_loss) <= 5e-4 * abs(ref_loss), (step, float(loss), ref_loss)
+    ref_sd = model.state_dict()
+    for k in keys:
+        torch.testing.assert_close(sd[k].detach(), ref_sd[k], rtol=1e-3, atol=1e-5, msg=k)
