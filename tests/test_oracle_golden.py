@@ -10,6 +10,10 @@ from conftest import golden_graph
 RTOL = 2e-5   # fp32 CPU vs fp32 CPU, different summation order only
 
 
+def _pre_bn_bias(k):
+    return k in ("patient_transform.0.bias", "patient_transform.4.bias") or k.endswith("lin_l.bias")
+
+
 def _clone(sd):
     return {k: v.clone() for k, v in sd.items()}
 
@@ -35,6 +39,9 @@ def test_oracle_train_step_matches_reference(fixture, request):
     none_keys = sorted(k for k, v in grads.items() if v is None)
     assert none_keys == blob["grad_is_none"]
     for k, gn in blob["grad_norm"].items():
+        if _pre_bn_bias(k):     # true gradient is exactly 0 (BatchNorm removes the mean): rounding noise only
+            assert gn < 1e-6 and float(grads[k].double().norm()) < 1e-6, k
+            continue
         assert abs(float(grads[k].double().norm()) - gn) <= 1e-4 * gn + 1e-9, k
     for k, gref in blob["grads"].items():
         torch.testing.assert_close(grads[k], gref, rtol=1e-4, atol=1e-7 + 1e-4 * float(gref.abs().max()), msg=k)
