@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the hetero-GNN training hot path (BASELINE.json metric: train edges/sec, fwd+bwd, per
+HeteroConv step; workload: configs[1], the MIMIC-III-shaped synthetic graph "C2").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+
+One "step" = one full training step of the reference's Trainer.train_epoch (train.py:332-392) on the
+full graph: encode -> 2 x HeteroConv/BN/ReLU -> gated decoder over all train-split pairs -> weighted
+loss over the 20 % supervised pairs -> backward -> Adam.  The unit of work is a *directed edge of one
+HeteroConv layer application*: L * 2(E_l+E_d+E_m) per step.
+
+value : device-timed (CUDA events), step inputs already resident in HBM.
+e2e   : the same step through the public Trainer API with HOST inputs: the step's pair indices, targets and
+        supervision mask are copied from pinned host memory every step and the loss is read back.
+roofline : dominant libb2g kernel of one instrumented step (CUDA events around every library call).
+cpu_baseline : the oracle port (oracle/hetero_rgcn_ref.py, torch CPU, all host threads) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "multi-modal-gnn_b200"
+METRIC = "train_edges_per_sec_fwd_bwd_per_heteroconv_step"
+UNIT = "directed-edge-layer traversals/s"
+NUM_LAYERS = 2
+
+
+def _cfg(dropout=0.2, loss="mse"):
+    return {"model": {"architecture": "RGCN", "hidden_dim": 128, "num_layers": NUM_LAYERS, "dropout": dropout,
+                      "use_batch_norm": True, "activation": "relu"},
+            "train": {"mask_fraction": 0.2, "train_split": 0.7, "val_split": 0.15, "test_split": 0.15, "loss": loss,
+                      "epochs": 100, "early_stopping_patience": 15,
+                      "optimizer": {"type": "adam", "lr": 1e-3, "weight_decay": 1e-5},
+                      "lr_scheduler": {"enabled": True, "type": "reduce_on_plateau", "factor": 0.5, "patience": 10},
+                      "seed": 42}}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm": float(p["hbm_gbs"]), "tensor_burst": float(p["bf16_tflops"]),
+                "tensor_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on a bounded sample of the workload
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_baseline_run(workload: str, steps: int, warmup: int, shrink: int = 16, loss: str = "mse"):
+    """Times oracle train steps (forward + weighted loss + backward + Adam, dropout 0.2 like the shipped config)
+    on a 1/shrink patient sample of the workload, with every host thread.  Returns (edges_per_s, ms, sample)."""
+    import torch
+    pkg = importlib.import_module(PKG)
+    from oracle import hetero_rgcn_ref as R
+    spec = pkg.synth.SPECS[workload]
+    small = pkg.synth.GraphSpec(spec.name + f"/{shrink}", max(spec.n_patient // shrink, 64), spec.n_lab, spec.n_dx, spec.n_med,
+                                spec.e_lab // shrink, spec.e_dx // shrink, spec.e_med // shrink, spec.low_degree_frac)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = pkg.synth.make_graph(small, seed=42)
+    counts = {nt: int(g[nt].num_nodes) for nt in g.node_types}
+    ets = list(g.edge_types)
+    sd = R.init_state(counts, ets, seed=0)
+    ei = g["patient", "has_lab", "lab"].edge_index
+    attr = g["patient", "has_lab", "lab"].edge_attr
+    tr = R.split_masks(ei.shape[1])[0]
+    pi, li, tgt = ei[0][tr], ei[1][tr], attr[tr].squeeze(-1)
+    w = R.lab_weights(li, tgt, counts["lab"])
+    keys = R.trainable_keys(sd)
+    params = [sd[k].requires_grad_(True) for k in keys]
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-5)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        sup = R.supervision_mask(int(tr.sum()), 0.2, 1000 + it)
+        opt.zero_grad()
+        pred = R.predict_lab_values(sd, counts, ets, g.edge_index_dict, pi, li, True, p_drop=0.2)
+        lossv = R.weighted_loss(pred, tgt, li, w, sup, loss)
+        lossv.backward()
+        opt.step()
+        float(lossv.detach())
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    edges = NUM_LAYERS * small.directed_edges_per_layer
+    sample = (f"{workload} shrunk 1/{shrink}: {small.n_patient} patients, {small.e_lab}/{small.e_dx}/{small.e_med} edges, "
+              f"median of {steps} oracle train steps after {warmup} warm-up")
+    return edges / t, t * 1e3, sample, cores
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  /root/reference is absent on the GPU
+    box and PyG is not installable, so this is the oracle port (kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, ms, sample, cores = cpu_baseline_run(args.workload, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = os.path.join("/tmp", f"b2g_clocks_{os.getpid()}.csv")
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1])); mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)
+    ops = importlib.import_module(PKG + ".ops")
+    M = importlib.import_module(PKG + ".model")
+    T = importlib.import_module(PKG + ".trainer")
+    L = importlib.import_module(PKG + "._lib")
+    lib = L.load()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec = pkg.synth.SPECS[args.workload]
+    cfg = _cfg(dropout=0.2, loss="mse")
+    # weak scaling: every rank owns an independent patient partition of the same shape (replicated type tables);
+    # see DESIGN.md section Multi-GPU for what is and is not synchronised in this round.
+    g_host = pkg.synth.make_graph(spec, seed=42 + rank)
+    masker = T.EdgeMasker(g_host, 0.7, 0.15, 0.15, 0.2, 42)
+    model = M.build_model(cfg, (g_host.node_types, g_host.edge_types), None)
+    trainer = T.Trainer(model, g_host, masker, cfg, dev)
+    model._init_embeddings(trainer.data)          # tables exist before the first timed step (lazy init is not timed)
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+
+    pi, li = masker.split_rows("train")
+    _, ev = masker.split_edges("train")
+    n_train = int(pi.numel())
+    total_steps = args.warmup + args.steps
+    sup_host = [masker.supervision_mask("train", seed=1000 + i).pin_memory() for i in range(total_steps)]
+    sup_dev = [s.to(dev) for s in sup_host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def allreduce_grads():
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in model.parameters():
+                if p.grad is not None:
+                    n = p.grad.numel()
+                    p.grad.copy_(flat[off:off + n].view_as(p.grad)); off += n
+
+    def step_device(i):
+        trainer.optimizer.zero_grad()
+        pred = model.predict_lab_values(trainer.data, pi, li)
+        loss = ops.weighted_loss(pred, ev, li, trainer.lab_weights, sup_dev[i], "mse")
+        loss.backward()
+        allreduce_grads()
+        trainer.optimizer.step()
+        return loss
+
+    model.train()
+    # ---- warm-up ----
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+
+    # ---- timed: device-resident inputs ----
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib.b2g_reset_launch_count()
+    evs = []
+    for i in range(args.warmup, total_steps):
+        flush.fill_(i & 0xFF)                       # L2 flush (256 MiB write) outside the per-step events
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        loss = step_device(i)
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = int(lib.b2g_launch_count())
+    step_ms = [s.elapsed_time(e) for s, e in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    final_loss = float(loss.item())
+
+    # ---- timed: end to end through the public Trainer API with host inputs ----
+    pi_h, li_h, ev_h = pi.cpu().pin_memory(), li.cpu().pin_memory(), ev.cpu().pin_memory()
+    pi_d, li_d, ev_d = torch.empty_like(pi), torch.empty_like(li), torch.empty_like(ev)
+    sup_d = torch.empty(n_train, dtype=torch.bool, device=dev)
+    h2d = pi_h.numel() * 8 + li_h.numel() * 8 + ev_h.numel() * 4 + n_train
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def step_e2e(i):
+        pi_d.copy_(pi_h, non_blocking=True); li_d.copy_(li_h, non_blocking=True)
+        ev_d.copy_(ev_h, non_blocking=True); sup_d.copy_(sup_host[i % total_steps], non_blocking=True)
+        loss = trainer.train_step(pi_d, li_d, ev_d, sup_d)
+        return float(loss.item())                  # device -> host read of the step's result
+
+    step_e2e(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t.item()) * 1e3 / e2e_steps
+
+    # ---- one instrumented step: per-kernel CUDA-event durations -> dominant kernel + roofline ----
+    roof, kernels = None, None
+    if rank == 0:
+        ops.PROFILE = []
+        flush.fill_(1)
+        step_device(args.warmup)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for name, s, e, nbytes, flops in prof:
+            a = agg.setdefault(name, [0.0, 0, 0, 0])
+            a[0] += s.elapsed_time(e); a[1] += 1; a[2] += nbytes; a[3] += flops
+        tot = sum(a[0] for a in agg.values())
+        kernels = {k: {"ms": round(a[0], 4), "calls": a[1], "share": round(a[0] / tot, 4),
+                       "GBps": round(a[2] / a[0] / 1e6, 1) if a[0] > 0 else None,
+                       "TFLOPs": round(a[3] / a[0] / 1e9, 2) if a[0] > 0 else None}
+                   for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        top = max(agg.items(), key=lambda kv: kv[1][0])
+        peaks = _peaks()
+        name, (ms, calls, nbytes, flops) = top[0], top[1]
+        ach = nbytes / calls / (ms / calls * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                "traffic": None, "launches_per_step": calls, "avg_launch_ms": ms / calls, "share_of_step": a_share(ms, tot),
+                "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if peaks["source"] == "measured" else "fallback"}
+
+    if rank == 0:
+        edges_per_step = NUM_LAYERS * spec.directed_edges_per_layer * world
+        line = {"metric": METRIC, "value": edges_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {spec.n_patient} patients/{spec.n_lab} labs/{spec.n_dx} dx/{spec.n_med} meds, "
+                                       f"{spec.e_lab}/{spec.e_dx}/{spec.e_med} edges per GPU, d=128, L=2, dropout 0.2, mse + lab weights, "
+                                       f"{n_train} train pairs, 20% supervised, Adam",
+                           "step": "Trainer.train_epoch body: predict_lab_values fwd + weighted loss + bwd + Adam",
+                           "l2": "flushed with a 256 MiB write before every timed step; per-step working set (>1 GB) also exceeds the 126 MB L2",
+                           "parallelism": f"patient-partitioned x{world}" if world > 1 else "single GPU"},
+                "e2e": {"value": edges_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels, "final_loss": final_loss,
+                "step_ms_min_max": [min(step_ms), max(step_ms)]}
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, sample, cores = cpu_baseline_run(args.workload, 3, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def a_share(ms, tot):
+    return round(ms / tot, 4) if tot > 0 else None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+/*
+ * b2g.h -- C ABI of libb2g.so: the B200 (sm_100a) kernels behind the hetero-GNN training / imputation
+ * hot path of AdalineL/Multi-Modal-GNN (reference: /root/reference/src/model.py, src/train.py).
+ *
+ * The reference has no FFI of its own (pure Python; all arithmetic in the torch / torch-geometric wheels),
+ * so the boundary is: the Python surface of src/model.py (kept by multi-modal-gnn_b200/model.py) on top of
+ * THIS library.  Every entry point below names the reference expression it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch types; all pointers are DEVICE pointers unless named h_*;
+ *   - every function returns 0 on success, a negative B2G_E* code otherwise; b2g_last_error() gives text;
+ *   - nothing allocates or frees caller memory; scratch space is passed in (`ws`, size from *_ws_bytes);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation unless
+ *     stated ("SYNC");
+ *   - feature matrices are row-major fp32 [rows, d], 16-byte aligned, d in {32, 64, 128, 256};
+ *   - indices inside the library are int32 (E < 2^31, rows < 2^31); row*d offsets are 64-bit;
+ *   - results are deterministic (run-to-run bit-identical): no floating-point atomics anywhere.
+ */
+#ifndef B2G_H_
+#define B2G_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2G_OK 0
+#define B2G_EINVAL (-1)   /* bad argument (shape, alignment, null pointer)                     */
+#define B2G_ECUDA (-2)    /* a CUDA runtime call failed                                        */
+#define B2G_ERANGE (-3)   /* an edge endpoint is outside [0, n) -- graph_build.py:611-633       */
+#define B2G_EWS (-4)      /* workspace too small                                               */
+
+const char* b2g_last_error(void);
+int b2g_version(void);
+/* number of kernels this library has launched since load / since reset (bench.py's gpu_launches) */
+unsigned long long b2g_launch_count(void);
+void b2g_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a) graph structure -- replaces PyG's COO index_select/scatter bookkeeping
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Stable CSR of one relation, keyed by `key` (the destination for a forward CSR, the source for the
+ * transposed one).  Input is the reference's COO layout: edge_index[2,E] int64 (graph_build.py:515),
+ * key = edge_index[1] or [0], val = the other row.
+ *   rowptr[n_rows+1]  exclusive prefix of the per-row edge counts (bit-exact torch.bincount / cumsum)
+ *   col[E]            val[] reordered so that row r owns col[rowptr[r] .. rowptr[r+1])
+ *   eid[E]            original edge position of each slot; within a row, eid is increasing (stable)
+ * ws: b2g_csr_build_ws_bytes(E, n_rows) bytes.  Returns B2G_ERANGE (after a SYNC on `stream`) if any
+ * key is outside [0,n_rows) or any val outside [0,n_vals) -- mirrors validate_graph's ValueError. */
+size_t b2g_csr_build_ws_bytes(int64_t n_edges, int64_t n_rows);
+int b2g_csr_build(const int64_t* key, const int64_t* val, int64_t n_edges, int64_t n_rows, int64_t n_vals,
+                  int32_t* rowptr, int32_t* col, int32_t* eid, void* ws, size_t ws_bytes, void* stream);
+
+/* deg[r] = rowptr[r+1]-rowptr[r] as int64  == torch.bincount(edge_index[0], minlength=N) (model.py:297-298)
+ * inv[r] = 1 / max(deg[r], 1) as fp32      == PyG mean aggregation's clamp(count, min=1) reciprocal */
+int b2g_csr_degrees(const int32_t* rowptr, int64_t n_rows, int64_t* deg, float* inv, void* stream);
+
+/* low[i] = deg[patient_idx[i]] < threshold (uint8 0/1)     model.py:312-315 (threshold 6, model.py:178) */
+int b2g_degree_gate(const int64_t* deg, const int64_t* patient_idx, int64_t m, int64_t threshold,
+                    uint8_t* low, void* stream);
+
+/* Work decomposition for rows that are too long for one warp (type-destination rows own up to millions
+ * of patient neighbours).  Row r is cut into max(1, ceil(deg/chunk)) items; item i of row item_row[i]
+ * covers CSR slots [item_start[i], min(item_start[i]+chunk, rowptr[row+1])); row r owns items
+ * [row_item_ptr[r], row_item_ptr[r+1]).  _count fills row_item_ptr[n_rows+1] and returns the number of
+ * items in *h_n_items (SYNC); _fill then writes item_row / item_start (n_items entries each). */
+size_t b2g_csr_chunk_ws_bytes(int64_t n_rows);
+int b2g_csr_chunk_count(const int32_t* rowptr, int64_t n_rows, int32_t chunk, int32_t* row_item_ptr,
+                        int64_t* h_n_items, void* ws, size_t ws_bytes, void* stream);
+int b2g_csr_chunk_fill(const int32_t* rowptr, int64_t n_rows, int32_t chunk, const int32_t* row_item_ptr,
+                       int32_t* item_row, int32_t* item_start, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (b) message passing -- replaces SAGEConv.propagate: index_select + scatter_add + /clamp(count,1)
+ *     (PyG sage_conv.py / utils/scatter.py; call sites model.py:125-131,256)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One relation of a fused gather-reduce. */
+typedef struct {
+  const int32_t* rowptr;     /* [n_rows+1] CSR keyed by the OUTPUT row                          */
+  const int32_t* col;        /* [E] neighbour row in `x`                                        */
+  const float* x;            /* [n_x, d] neighbour features                                     */
+  const float* row_scale;    /* [n_rows] or NULL: multiplies the reduced row (1/deg for a mean)  */
+  const float* col_scale;    /* [n_x]    or NULL: multiplies each gathered row (transposed mean) */
+} b2g_rel_t;
+
+/* out[r,:] = (accumulate ? out[r,:] : 0) + sum_k row_scale_k[r] * sum_{j in row r of rel k}
+ *            col_scale_k[col[j]] * x_k[col[j], :]
+ * Warp-per-row segmented gather-reduce, 128-bit row loads, up to 4 relations fused (patient
+ * destinations: lab + diagnosis + medication neighbours in one pass over the patient rows).
+ * Intended for SHORT rows (degree <= a few hundred). */
+int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_rows, int d, float* out,
+                      int accumulate, void* stream);
+
+/* Same contraction for LONG rows (type destinations).  Two deterministic phases: one warp per chunk
+ * item writes a partial row into ws, then one warp per output row adds its partials in item order.
+ * ws: n_items * d * 4 bytes. */
+int b2g_gather_reduce_chunked(const b2g_rel_t* h_rel, const int32_t* item_row, const int32_t* item_start,
+                              const int32_t* row_item_ptr, int64_t n_items, int32_t chunk, int64_t n_rows,
+                              int d, float* out, int accumulate, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (c) embedding tables -- nn.Embedding(arange(N)) fwd / dense grad (model.py:225-226)
+ * ---------------------------------------------------------------------------------------------- */
+/* out[i,:] = table[idx[i],:]   (idx int64, as the reference passes them) */
+int b2g_gather_rows(const float* table, const int64_t* idx, int64_t m, int64_t n_table, int d, float* out,
+                    void* stream);
+/* fused decoder input: out[i,:] = act(a[ia[i],:] + b[ib[i],:]) with act = ReLU (optional) */
+int b2g_gather_add_rows(const float* a, const int64_t* ia, const float* b, const int64_t* ib, int64_t m,
+                        int d, int relu, float* out, void* stream);
+
+/* out[idx[i]] = vals[i] / out[i] = src[idx[i]] for fp32 scalars: assembling the per-head predictions into
+ * predictions[M] (model.py:317-333 masked writes) and its backward. idx entries must be unique for scatter. */
+int b2g_scatter_values(const float* vals, const int64_t* idx, int64_t m, float* out, void* stream);
+int b2g_gather_values(const float* src, const int64_t* idx, int64_t m, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (d) dense layers -- nn.Linear / SAGEConv.lin_l / lin_r / EdgeRegressionHead (model.py:93-103,373-386)
+ * ---------------------------------------------------------------------------------------------- */
+/* y[M,N] = (accumulate ? y : 0) + x[M,K] * w[N,K]^T + bias[N]   (bias may be NULL)  fp32 SIMT */
+int b2g_linear_fwd(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y,
+                   int accumulate, void* stream);
+/* dx[M,K] = (accumulate ? dx : 0) + dy[M,N] * w[N,K] */
+int b2g_linear_bwd_input(const float* dy, const float* w, int64_t m, int n, int k, float* dx, int accumulate,
+                         void* stream);
+/* dw[N,K] = dy[M,N]^T * x[M,K];  db[N] = column sums of dy (db may be NULL).  Deterministic split over M.
+ * ws: b2g_linear_bwd_weight_ws_bytes(m, n, k). */
+size_t b2g_linear_bwd_weight_ws_bytes(int64_t m, int n, int k);
+int b2g_linear_bwd_weight(const float* dy, const float* x, int64_t m, int n, int k, float* dw, float* db,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (d') BatchNorm1d + ReLU + Dropout, row L2 normalisation (model.py:93-105,134-139,259-269)
+ * ---------------------------------------------------------------------------------------------- */
+/* Batch statistics of x[M,d] (training mode): mean[d], rstd[d] = 1/sqrt(biased var + eps); optionally
+ * updates running_mean / running_var in place with `momentum` and the UNBIASED variance, like
+ * nn.BatchNorm1d.  fp64 accumulation, two deterministic stages.  ws: b2g_bn_ws_bytes(d). */
+size_t b2g_bn_ws_bytes(int d);
+int b2g_bn_stats(const float* x, int64_t m, int d, float eps, float momentum, float* mean, float* rstd,
+                 float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream);
+/* eval mode: mean = running_mean, rstd = 1/sqrt(running_var + eps) */
+int b2g_bn_eval_stats(const float* running_mean, const float* running_var, int d, float eps, float* mean,
+                      float* rstd, void* stream);
+/* y = dropout(act((x - mean) * rstd * gamma + beta)); `relu` is the activation code of model.py:145-153:
+ * 0 none, 1 relu, 2 leaky_relu(0.01), 3 elu(1.0); dropout optional (p_drop == 0 -> none).
+ * The keep mask is Philox4x32-10(seed, stream_id) per element, scaled by 1/(1-p) (F.dropout semantics). */
+int b2g_bn_apply(const float* x, int64_t m, int d, const float* mean, const float* rstd, const float* gamma,
+                 const float* beta, int relu, float p_drop, uint64_t seed, uint64_t stream_id, float* y,
+                 void* stream);
+/* backward of the above.  Phase 1 (train mode only) reduces dgamma = sum(g * xhat), dbeta = sum(g) with
+ * g = dy * mask * relu'; phase 2 writes dx.  In eval mode (batch_stats == 0) dx = g * gamma * rstd. */
+int b2g_bn_bwd(const float* x, const float* dy, int64_t m, int d, const float* mean, const float* rstd,
+               const float* gamma, const float* beta, int relu, float p_drop, uint64_t seed,
+               uint64_t stream_id, int batch_stats, float* dx, float* dgamma, float* dbeta, void* ws,
+               size_t ws_bytes, void* stream);
+/* y = dropout(relu(x)) without normalisation (EdgeRegressionHead, model.py:377-380) and its backward
+ * (dx = dy * mask * [y > 0]); in-place allowed. */
+int b2g_relu_dropout_fwd(const float* x, int64_t n, int relu, float p_drop, uint64_t seed, uint64_t stream_id,
+                         float* y, void* stream);
+int b2g_relu_dropout_bwd(const float* y, const float* dy, int64_t n, int relu, float p_drop, uint64_t seed,
+                         uint64_t stream_id, float* dx, void* stream);
+/* the keep mask alone (0 or 1/(1-p)), for replaying device dropout on the CPU oracle */
+int b2g_dropout_mask(int64_t n, float p_drop, uint64_t seed, uint64_t stream_id, float* mask, void* stream);
+
+/* y[r,:] = x[r,:] / max(||x[r,:]||_2, eps); inv_norm[r] saved for backward  (F.normalize, model.py:232) */
+int b2g_l2norm_fwd(const float* x, int64_t m, int d, float eps, float* y, float* inv_norm, void* stream);
+int b2g_l2norm_bwd(const float* y, const float* dy, const float* inv_norm, int64_t m, int d, float* dx,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (e) loss -- train.py:364-386 weighted MAE / MSE over the supervised subset, model.py:602-605
+ * ---------------------------------------------------------------------------------------------- */
+/* loss = (1/n_sup) * sum_{i: sup[i]} w[lab[i]] * (|p-t| or (p-t)^2); grad[i] = dloss/dpred[i] (0 where
+ * !sup[i]).  sup / w may be NULL (all edges, unit weights).  kind: 0 = mae, 1 = mse, 2 = huber(delta 1).
+ * Deterministic tree reduction.  ws: b2g_loss_ws_bytes(m). */
+size_t b2g_loss_ws_bytes(int64_t m);
+int b2g_weighted_loss(const float* pred, const float* target, const int64_t* lab, const float* w,
+                      const uint8_t* sup, int64_t m, int kind, float* loss, float* grad, void* ws,
+                      size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2G_H_ */

@@ -1,0 +1,506 @@
+// BatchNorm1d (+ReLU +Dropout) forward/backward, row L2 normalisation, ReLU/Dropout, weighted loss.
+// Reference ops: nn.BatchNorm1d / F.relu / F.dropout / F.normalize (model.py:93-105,134-139,259-269),
+// weighted MAE/MSE (train.py:364-386), compute_regression_loss (model.py:579-612).
+// All reductions are two-stage and order-fixed (deterministic); column statistics accumulate in fp64.
+#include "common.cuh"
+
+namespace {
+using namespace b2g;
+
+constexpr int MAX_PARTIALS = 592;  // 4 x 148 CTAs
+
+// activation codes (model.py:145-153): 0 none, 1 relu, 2 leaky_relu(0.01), 3 elu(alpha 1)
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v > 0.f ? v : 0.01f * v;
+  if (act == 3) return v > 0.f ? v : expm1f(v);
+  return v;
+}
+__device__ __forceinline__ float act_grad(float pre, int act) {
+  if (act == 1) return pre > 0.f ? 1.f : 0.f;
+  if (act == 2) return pre > 0.f ? 1.f : 0.01f;
+  if (act == 3) return pre > 0.f ? 1.f : expf(pre);
+  return 1.f;
+}
+
+// ---- column reductions ------------------------------------------------------------------------------------------
+// MODE 0: s0 = sum x,        s1 = sum x^2                    (batch statistics)
+// MODE 1: s0 = sum g,        s1 = sum g * xhat                (BN backward), g = dy * dropmask * relu'
+template <int MODE>
+__global__ void __launch_bounds__(256) k_col_partial(const float* __restrict__ x, const float* __restrict__ dy, int64_t m, int d,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta, int relu, float p_drop,
+                                                     uint64_t seed, uint64_t sid, double* __restrict__ partial) {
+  extern __shared__ double sm[];  // [rows_per_pass][2][d]
+  const int tpr = d >> 2;               // threads per row (float4 each)
+  const int rpp = 256 / tpr;            // rows per pass of the block
+  const int cg = threadIdx.x % tpr, rs = threadIdx.x / tpr;
+  const int c = cg * 4;
+  double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+  float mu[4] = {0, 0, 0, 0}, rsd[4] = {1, 1, 1, 1}, ga[4] = {1, 1, 1, 1}, be[4] = {0, 0, 0, 0};
+  if (MODE == 1) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      mu[q] = mean[c + q]; rsd[q] = rstd[c + q]; ga[q] = gamma[c + q]; be[q] = beta[c + q];
+    }
+  }
+  for (int64_t r = (int64_t)blockIdx.x * rpp + rs; r < m; r += (int64_t)gridDim.x * rpp) {
+    const size_t off = (size_t)r * d + c;
+    float4 xv = ld_stream(reinterpret_cast<const float4*>(x + off));
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (MODE == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a0[q] += (double)xs[q];
+        a1[q] += (double)xs[q] * (double)xs[q];
+      }
+    } else {
+      float4 gv = ld_stream(reinterpret_cast<const float4*>(dy + off));
+      float g[4] = {gv.x, gv.y, gv.z, gv.w};
+      if (p_drop > 0.f) {
+        float4 mk = dropout_scale4(seed, sid, off >> 2, p_drop);
+        g[0] *= mk.x; g[1] *= mk.y; g[2] *= mk.z; g[3] *= mk.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float xh = (xs[q] - mu[q]) * rsd[q];
+        g[q] *= act_grad(fmaf(xh, ga[q], be[q]), relu);
+        a0[q] += (double)g[q];
+        a1[q] += (double)g[q] * (double)xh;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    sm[(size_t)(rs * 2 + 0) * d + c + q] = a0[q];
+    sm[(size_t)(rs * 2 + 1) * d + c + q] = a1[q];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * d; i += 256) {
+    int which = i / d, col = i % d;
+    double s = 0;
+    for (int rr = 0; rr < rpp; ++rr) s += sm[(size_t)(rr * 2 + which) * d + col];
+    partial[((size_t)blockIdx.x * 2 + which) * d + col] = s;
+  }
+}
+
+// stage 2 of MODE 0: mean / rstd (+ running-stat update like nn.BatchNorm1d in training mode)
+__global__ void k_bn_finalize(const double* __restrict__ partial, int n_part, int64_t m, int d, float eps, float momentum,
+                              float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
+                              float* __restrict__ running_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  double s0 = 0, s1 = 0;
+  for (int p = 0; p < n_part; ++p) {
+    s0 += partial[((size_t)p * 2 + 0) * d + c];
+    s1 += partial[((size_t)p * 2 + 1) * d + c];
+  }
+  double mu = s0 / (double)m;
+  double var = s1 / (double)m - mu * mu;
+  if (var < 0) var = 0;
+  mean[c] = (float)mu;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+  if (running_var) {
+    double unb = m > 1 ? var * ((double)m / (double)(m - 1)) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+// stage 2 of MODE 1: totals -> sums[2][d] (double) and dbeta / dgamma
+__global__ void k_bn_bwd_finalize(const double* __restrict__ partial, int n_part, int d, double* __restrict__ sums, float* __restrict__ dgamma,
+                                  float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  double s0 = 0, s1 = 0;
+  for (int p = 0; p < n_part; ++p) {
+    s0 += partial[((size_t)p * 2 + 0) * d + c];
+    s1 += partial[((size_t)p * 2 + 1) * d + c];
+  }
+  sums[c] = s0;
+  sums[d + c] = s1;
+  if (dbeta) dbeta[c] = (float)s0;
+  if (dgamma) dgamma[c] = (float)s1;
+}
+
+__global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __restrict__ rv, int d, float eps, float* __restrict__ mean,
+                                float* __restrict__ rstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  mean[c] = rm[c];
+  rstd[c] = 1.0f / sqrtf(rv[c] + eps);
+}
+
+__global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ x, int64_t n4, int d, const float* __restrict__ mean,
+                                                  const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  int relu, float p_drop, uint64_t seed, uint64_t sid, float* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)((i * 4) % d);
+    float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + i);
+    float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 o;
+    o.x = fmaf((xv.x - mu.x) * rs.x, ga.x, be.x);
+    o.y = fmaf((xv.y - mu.y) * rs.y, ga.y, be.y);
+    o.z = fmaf((xv.z - mu.z) * rs.z, ga.z, be.z);
+    o.w = fmaf((xv.w - mu.w) * rs.w, ga.w, be.w);
+    o.x = act_fwd(o.x, relu); o.y = act_fwd(o.y, relu); o.z = act_fwd(o.z, relu); o.w = act_fwd(o.w, relu);
+    if (p_drop > 0.f) {
+      float4 mk = dropout_scale4(seed, sid, (uint64_t)i, p_drop);
+      o.x *= mk.x; o.y *= mk.y; o.z *= mk.z; o.w *= mk.w;
+    }
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, int64_t n4, int64_t m, int d,
+                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta, int relu, float p_drop,
+                                                      uint64_t seed, uint64_t sid, int batch_stats, const double* __restrict__ sums,
+                                                      float* __restrict__ dx) {
+  const float inv_m = 1.0f / (float)m;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)((i * 4) % d);
+    float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + i);
+    float4 gv = ld_stream(reinterpret_cast<const float4*>(dy) + i);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, g[4] = {gv.x, gv.y, gv.z, gv.w}, o[4];
+    if (p_drop > 0.f) {
+      float4 mk = dropout_scale4(seed, sid, (uint64_t)i, p_drop);
+      g[0] *= mk.x; g[1] *= mk.y; g[2] *= mk.z; g[3] *= mk.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float mu = __ldg(mean + c + q), rs = __ldg(rstd + c + q), ga = __ldg(gamma + c + q), be = __ldg(beta + c + q);
+      float xh = (xs[q] - mu) * rs;
+      g[q] *= act_grad(fmaf(xh, ga, be), relu);
+      if (batch_stats) {
+        float sg = (float)sums[c + q] * inv_m, sgx = (float)sums[d + c + q] * inv_m;
+        o[q] = ga * rs * (g[q] - sg - xh * sgx);
+      } else {
+        o[q] = ga * rs * g[q];
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- ReLU / Dropout --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_relu_dropout_fwd(const float* __restrict__ x, int64_t n, int relu, float p, uint64_t seed, uint64_t sid,
+                                                          float* __restrict__ y) {
+  const int64_t n4 = (n + 3) >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p > 0.f) mk = dropout_scale4(seed, sid, (uint64_t)i, p);
+    float mks[4] = {mk.x, mk.y, mk.z, mk.w};
+    if (i * 4 + 3 < n) {
+      float4 v = reinterpret_cast<const float4*>(x)[i];
+      float vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) vs[q] = (relu ? fmaxf(vs[q], 0.f) : vs[q]) * mks[q];
+      reinterpret_cast<float4*>(y)[i] = make_float4(vs[0], vs[1], vs[2], vs[3]);
+    } else {
+      for (int q = 0; q < 4 && i * 4 + q < n; ++q) {
+        float v = x[i * 4 + q];
+        y[i * 4 + q] = (relu ? fmaxf(v, 0.f) : v) * mks[q];
+      }
+    }
+  }
+}
+
+// dx = dy * mask * [y > 0]  (y is the forward OUTPUT: y > 0 <=> pre-activation > 0 and kept)
+__global__ void __launch_bounds__(256) k_relu_dropout_bwd(const float* __restrict__ y, const float* __restrict__ dy, int64_t n, int relu, float p,
+                                                          uint64_t seed, uint64_t sid, float* __restrict__ dx) {
+  const int64_t n4 = (n + 3) >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p > 0.f) mk = dropout_scale4(seed, sid, (uint64_t)i, p);
+    float mks[4] = {mk.x, mk.y, mk.z, mk.w};
+    for (int q = 0; q < 4 && i * 4 + q < n; ++q) {
+      int64_t e = i * 4 + q;
+      float g = dy[e] * mks[q];
+      if (relu && !(y[e] > 0.f)) g = 0.f;
+      dx[e] = g;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dropout_mask(int64_t n, float p, uint64_t seed, uint64_t sid, float* __restrict__ mask) {
+  const int64_t n4 = (n + 3) >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p > 0.f) mk = dropout_scale4(seed, sid, (uint64_t)i, p);
+    float mks[4] = {mk.x, mk.y, mk.z, mk.w};
+    for (int q = 0; q < 4 && i * 4 + q < n; ++q) mask[i * 4 + q] = mks[q];
+  }
+}
+
+// ---- row L2 normalisation -----------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_l2norm_fwd(const float* __restrict__ x, int64_t m, float eps, float* __restrict__ y,
+                                                    float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= m) return;
+  RowVec<D> v;
+  v.load(x + (size_t)r * D, lane);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowVec<D>::N; ++i) ss = fmaf(v.v[i], v.v[i], ss);
+  ss = warp_sum(ss);
+  float inv = 1.0f / fmaxf(sqrtf(ss), eps);
+#pragma unroll
+  for (int i = 0; i < RowVec<D>::N; ++i) v.v[i] *= inv;
+  v.store(y + (size_t)r * D, lane);
+  if (lane == 0) inv_norm[r] = inv;
+}
+
+// y = x * inv  =>  dx = inv * (dy - y * <y, dy>)      (rows clamped by eps have <.,.> ~ 0 and reduce to inv * dy)
+template <int D>
+__global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ y, const float* __restrict__ dy, const float* __restrict__ inv_norm,
+                                                    int64_t m, float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= m) return;
+  RowVec<D> yv, gv;
+  yv.load(y + (size_t)r * D, lane);
+  gv.load(dy + (size_t)r * D, lane);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowVec<D>::N; ++i) dot = fmaf(yv.v[i], gv.v[i], dot);
+  dot = warp_sum(dot);
+  float inv = __ldg(inv_norm + r);
+#pragma unroll
+  for (int i = 0; i < RowVec<D>::N; ++i) gv.v[i] = inv * (gv.v[i] - yv.v[i] * dot);
+  gv.store(dx + (size_t)r * D, lane);
+}
+
+// ---- loss -----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float loss_term(float diff, int kind) {
+  float a = fabsf(diff);
+  if (kind == 0) return a;
+  if (kind == 1) return diff * diff;
+  return a < 1.f ? 0.5f * diff * diff : a - 0.5f;
+}
+__device__ __forceinline__ float loss_dterm(float diff, int kind) {
+  float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+  if (kind == 0) return sgn;
+  if (kind == 1) return 2.f * diff;
+  return fabsf(diff) < 1.f ? diff : sgn;
+}
+
+__global__ void __launch_bounds__(256) k_loss_partial(const float* __restrict__ pred, const float* __restrict__ target,
+                                                      const int64_t* __restrict__ lab, const float* __restrict__ w, const uint8_t* __restrict__ sup,
+                                                      int64_t m, int kind, double* __restrict__ part_sum, unsigned long long* __restrict__ part_cnt) {
+  __shared__ double ss[8];
+  __shared__ unsigned long long sc[8];
+  double s = 0;
+  unsigned long long cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    if (sup && !sup[i]) continue;
+    float wt = w ? __ldg(w + __ldg(lab + i)) : 1.f;
+    s += (double)(wt * loss_term(pred[i] - target[i], kind));
+    ++cnt;
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+  if ((threadIdx.x & 31) == 0) {
+    ss[threadIdx.x >> 5] = s;
+    sc[threadIdx.x >> 5] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    unsigned long long c = 0;
+    for (int i = 0; i < 8; ++i) {
+      t += ss[i];
+      c += sc[i];
+    }
+    part_sum[blockIdx.x] = t;
+    part_cnt[blockIdx.x] = c;
+  }
+}
+
+__global__ void k_loss_final(const double* __restrict__ part_sum, const unsigned long long* __restrict__ part_cnt, int n_part,
+                             float* __restrict__ loss, double* __restrict__ inv_count) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double t = 0;
+  unsigned long long c = 0;
+  for (int i = 0; i < n_part; ++i) {
+    t += part_sum[i];
+    c += part_cnt[i];
+  }
+  double inv = 1.0 / (double)c;  // c == 0 -> inf -> loss NaN, like torch's mean over an empty selection
+  *loss = (float)(t * inv);
+  *inv_count = inv;
+}
+
+__global__ void __launch_bounds__(256) k_loss_grad(const float* __restrict__ pred, const float* __restrict__ target, const int64_t* __restrict__ lab,
+                                                   const float* __restrict__ w, const uint8_t* __restrict__ sup, int64_t m, int kind,
+                                                   const double* __restrict__ inv_count, float* __restrict__ grad) {
+  const float inv = (float)(*inv_count);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = 0.f;
+    if (!sup || sup[i]) {
+      float wt = w ? __ldg(w + __ldg(lab + i)) : 1.f;
+      g = wt * loss_dterm(pred[i] - target[i], kind) * inv;
+    }
+    grad[i] = g;
+  }
+}
+
+inline int ew_grid(int64_t n_items) {
+  int64_t g = ceil_div(n_items, 256);
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+inline int col_parts(int64_t m, int d) {
+  int rpp = 256 / (d / 4);
+  int64_t g = ceil_div(m, (int64_t)rpp * 8);
+  return (int)(g < 1 ? 1 : (g > MAX_PARTIALS ? MAX_PARTIALS : g));
+}
+inline bool d_ok(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
+}  // namespace
+
+extern "C" size_t b2g_bn_ws_bytes(int d) { return align_up((size_t)MAX_PARTIALS * 2 * d * 8, 256) + align_up((size_t)2 * d * 8, 256); }
+
+extern "C" int b2g_bn_stats(const float* x, int64_t m, int d, float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                            float* running_var, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(x && mean && rstd && m > 0 && d_ok(d) && aligned16(x), "bn_stats: bad args (m=%lld d=%d)", (long long)m, d);
+  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
+    set_error("bn_stats: workspace too small");
+    return B2G_EWS;
+  }
+  double* partial = (double*)ws;
+  int parts = col_parts(m, d);
+  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
+  k_col_partial<0><<<parts, 256, smem, st>>>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, partial);
+  B2G_LAUNCH_CHECK();
+  k_bn_finalize<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(partial, parts, m, d, eps, momentum, mean, rstd, running_mean, running_var);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_bn_eval_stats(const float* running_mean, const float* running_var, int d, float eps, float* mean, float* rstd,
+                                 void* stream_) {
+  B2G_CHECK_ARG(running_mean && running_var && mean && rstd && d > 0, "bn_eval_stats: bad args");
+  k_bn_eval_stats<<<(unsigned)ceil_div(d, 128), 128, 0, (cudaStream_t)stream_>>>(running_mean, running_var, d, eps, mean, rstd);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_bn_apply(const float* x, int64_t m, int d, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                            int relu, float p_drop, uint64_t seed, uint64_t stream_id, float* y, void* stream_) {
+  B2G_CHECK_ARG(m >= 0 && d_ok(d) && (m == 0 || (x && y && mean && rstd && gamma && beta)), "bn_apply: bad args");
+  B2G_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "bn_apply: dropout p must be in [0,1)");
+  if (m == 0) return B2G_OK;
+  B2G_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
+                "bn_apply: unaligned pointer");
+  int64_t n4 = m * d / 4;
+  k_bn_apply<<<ew_grid(n4), 256, 0, (cudaStream_t)stream_>>>(x, n4, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, y);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_bn_bwd(const float* x, const float* dy, int64_t m, int d, const float* mean, const float* rstd, const float* gamma,
+                          const float* beta, int relu, float p_drop, uint64_t seed, uint64_t stream_id, int batch_stats, float* dx,
+                          float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(m > 0 && d_ok(d) && x && dy && mean && rstd && gamma && beta && dx, "bn_bwd: bad args");
+  B2G_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx), "bn_bwd: unaligned pointer");
+  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
+    set_error("bn_bwd: workspace too small");
+    return B2G_EWS;
+  }
+  double* partial = (double*)ws;
+  double* sums = (double*)((char*)ws + align_up((size_t)MAX_PARTIALS * 2 * d * 8, 256));
+  int parts = col_parts(m, d);
+  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
+  k_col_partial<1><<<parts, 256, smem, st>>>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, partial);
+  B2G_LAUNCH_CHECK();
+  k_bn_bwd_finalize<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(partial, parts, d, sums, dgamma, dbeta);
+  B2G_LAUNCH_CHECK();
+  int64_t n4 = m * d / 4;
+  k_bn_bwd_apply<<<ew_grid(n4), 256, 0, st>>>(x, dy, n4, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, batch_stats, sums, dx);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_relu_dropout_fwd(const float* x, int64_t n, int relu, float p_drop, uint64_t seed, uint64_t stream_id, float* y,
+                                    void* stream_) {
+  B2G_CHECK_ARG(n >= 0 && (n == 0 || (x && y)) && p_drop >= 0.f && p_drop < 1.f, "relu_dropout_fwd: bad args");
+  if (n == 0) return B2G_OK;
+  B2G_CHECK_ARG(aligned16(x) && aligned16(y), "relu_dropout_fwd: unaligned pointer");
+  k_relu_dropout_fwd<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream_>>>(x, n, relu, p_drop, seed, stream_id, y);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_relu_dropout_bwd(const float* y, const float* dy, int64_t n, int relu, float p_drop, uint64_t seed, uint64_t stream_id,
+                                    float* dx, void* stream_) {
+  B2G_CHECK_ARG(n >= 0 && (n == 0 || (y && dy && dx)) && p_drop >= 0.f && p_drop < 1.f, "relu_dropout_bwd: bad args");
+  if (n == 0) return B2G_OK;
+  k_relu_dropout_bwd<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream_>>>(y, dy, n, relu, p_drop, seed, stream_id, dx);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_dropout_mask(int64_t n, float p_drop, uint64_t seed, uint64_t stream_id, float* mask, void* stream_) {
+  B2G_CHECK_ARG(n >= 0 && (n == 0 || mask) && p_drop >= 0.f && p_drop < 1.f, "dropout_mask: bad args");
+  if (n == 0) return B2G_OK;
+  k_dropout_mask<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream_>>>(n, p_drop, seed, stream_id, mask);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_l2norm_fwd(const float* x, int64_t m, int d, float eps, float* y, float* inv_norm, void* stream_) {
+  B2G_CHECK_ARG(m >= 0 && (m == 0 || (x && y && inv_norm)), "l2norm_fwd: bad args");
+  if (m == 0) return B2G_OK;
+  B2G_CHECK_ARG(aligned16(x) && aligned16(y), "l2norm_fwd: unaligned pointer");
+  unsigned grid = (unsigned)ceil_div(m, 8);
+  DISPATCH_D(d, (k_l2norm_fwd<D><<<grid, 256, 0, (cudaStream_t)stream_>>>(x, m, eps, y, inv_norm)));
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_l2norm_bwd(const float* y, const float* dy, const float* inv_norm, int64_t m, int d, float* dx, void* stream_) {
+  B2G_CHECK_ARG(m >= 0 && (m == 0 || (y && dy && inv_norm && dx)), "l2norm_bwd: bad args");
+  if (m == 0) return B2G_OK;
+  B2G_CHECK_ARG(aligned16(y) && aligned16(dy) && aligned16(dx), "l2norm_bwd: unaligned pointer");
+  unsigned grid = (unsigned)ceil_div(m, 8);
+  DISPATCH_D(d, (k_l2norm_bwd<D><<<grid, 256, 0, (cudaStream_t)stream_>>>(y, dy, inv_norm, m, dx)));
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" size_t b2g_loss_ws_bytes(int64_t m) {
+  (void)m;
+  return align_up((size_t)MAX_PARTIALS * 8, 256) * 2 + 256;
+}
+
+extern "C" int b2g_weighted_loss(const float* pred, const float* target, const int64_t* lab, const float* w, const uint8_t* sup, int64_t m,
+                                 int kind, float* loss, float* grad, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(m >= 0 && loss && (m == 0 || (pred && target)) && kind >= 0 && kind <= 2 && (!w || lab), "weighted_loss: bad args");
+  if (!ws || ws_bytes < b2g_loss_ws_bytes(m)) {
+    set_error("weighted_loss: workspace too small");
+    return B2G_EWS;
+  }
+  double* part_sum = (double*)ws;
+  unsigned long long* part_cnt = (unsigned long long*)((char*)ws + align_up((size_t)MAX_PARTIALS * 8, 256));
+  double* inv_count = (double*)((char*)ws + 2 * align_up((size_t)MAX_PARTIALS * 8, 256));
+  int parts = (int)ceil_div(m > 0 ? m : 1, 256 * 8);
+  if (parts > MAX_PARTIALS) parts = MAX_PARTIALS;
+  k_loss_partial<<<parts, 256, 0, st>>>(pred, target, lab, w, sup, m, kind, part_sum, part_cnt);
+  B2G_LAUNCH_CHECK();
+  k_loss_final<<<1, 32, 0, st>>>(part_sum, part_cnt, parts, loss, inv_count);
+  B2G_LAUNCH_CHECK();
+  if (grad && m > 0) {
+    k_loss_grad<<<ew_grid(m), 256, 0, st>>>(pred, target, lab, w, sup, m, kind, inv_count, grad);
+    B2G_LAUNCH_CHECK();
+  }
+  return B2G_OK;
+}

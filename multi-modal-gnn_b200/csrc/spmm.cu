@@ -1,0 +1,232 @@
+// Segmented gather-reduce over CSR (the message-passing contraction) and row gathers.
+// Replaces SAGEConv.propagate's index_select -> [E,d] message tensor -> scatter_add (PyG; model.py:256):
+// no message tensor is ever materialised and no floating-point atomics are used.
+#include "common.cuh"
+
+namespace {
+using namespace b2g;
+
+struct RelPack {
+  b2g_rel_t r[4];
+};
+
+// sum_{j in [b,e)} col_scale[col[j]] * x[col[j],:]  accumulated into acc, edges visited in CSR order
+template <int D>
+__device__ __forceinline__ void reduce_span(const b2g_rel_t& rel, int b, int e, int lane, RowVec<D>& acc) {
+  for (int j0 = b; j0 < e; j0 += 32) {
+    int j = j0 + lane;
+    int my = (j < e) ? __ldg(rel.col + j) : 0;
+    float cs = (rel.col_scale != nullptr && j < e) ? __ldg(rel.col_scale + my) : 1.0f;
+    int cnt = min(32, e - j0);
+    int t = 0;
+    for (; t + 4 <= cnt; t += 4) {  // 4 independent row loads in flight
+      int c0 = __shfl_sync(FULL, my, t), c1 = __shfl_sync(FULL, my, t + 1), c2 = __shfl_sync(FULL, my, t + 2),
+          c3 = __shfl_sync(FULL, my, t + 3);
+      float s0 = __shfl_sync(FULL, cs, t), s1 = __shfl_sync(FULL, cs, t + 1), s2 = __shfl_sync(FULL, cs, t + 2),
+            s3 = __shfl_sync(FULL, cs, t + 3);
+      RowVec<D> r0, r1, r2, r3;
+      r0.load(rel.x + (size_t)c0 * D, lane);
+      r1.load(rel.x + (size_t)c1 * D, lane);
+      r2.load(rel.x + (size_t)c2 * D, lane);
+      r3.load(rel.x + (size_t)c3 * D, lane);
+      acc.fma(s0, r0);
+      acc.fma(s1, r1);
+      acc.fma(s2, r2);
+      acc.fma(s3, r3);
+    }
+    for (; t < cnt; ++t) {
+      int c = __shfl_sync(FULL, my, t);
+      float s = __shfl_sync(FULL, cs, t);
+      RowVec<D> r;
+      r.load(rel.x + (size_t)c * D, lane);
+      acc.fma(s, r);
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_gather_reduce(RelPack rels, int n_rels, int64_t n_rows, float* __restrict__ out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  RowVec<D> acc;
+  acc.zero();
+  for (int k = 0; k < n_rels; ++k) {
+    const b2g_rel_t& rel = rels.r[k];
+    int b = __ldg(rel.rowptr + row), e = __ldg(rel.rowptr + row + 1);
+    RowVec<D> part;
+    part.zero();
+    reduce_span<D>(rel, b, e, lane, part);
+    float rs = rel.row_scale ? __ldg(rel.row_scale + row) : 1.0f;
+    acc.fma(rs, part);
+  }
+  float* o = out + (size_t)row * D;
+  if (accumulate) {
+    RowVec<D> prev;
+    prev.load_rw(o, lane);
+    acc.add(prev);
+  }
+  acc.store(o, lane);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_chunk_partial(b2g_rel_t rel, const int32_t* __restrict__ item_row,
+                                                       const int32_t* __restrict__ item_start, int64_t n_items, int chunk,
+                                                       float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int64_t it = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (it >= n_items) return;
+  int row = __ldg(item_row + it);
+  int b = __ldg(item_start + it);
+  int e = min(b + chunk, __ldg(rel.rowptr + row + 1));
+  RowVec<D> acc;
+  acc.zero();
+  reduce_span<D>(rel, b, e, lane, acc);
+  acc.store(partial + (size_t)it * D, lane);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_chunk_final(const float* __restrict__ partial, const int32_t* __restrict__ row_item_ptr,
+                                                     const float* __restrict__ row_scale, int64_t n_rows, float* __restrict__ out,
+                                                     int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  int b = __ldg(row_item_ptr + row), e = __ldg(row_item_ptr + row + 1);
+  RowVec<D> acc;
+  acc.zero();
+  for (int i = b; i < e; ++i) {
+    RowVec<D> p;
+    p.load(partial + (size_t)i * D, lane);
+    acc.add(p);
+  }
+  float rs = row_scale ? __ldg(row_scale + row) : 1.0f;
+  RowVec<D> res;
+  res.zero();
+  res.fma(rs, acc);
+  float* o = out + (size_t)row * D;
+  if (accumulate) {
+    RowVec<D> prev;
+    prev.load_rw(o, lane);
+    res.add(prev);
+  }
+  res.store(o, lane);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ table, const int64_t* __restrict__ idx, int64_t m,
+                                                     float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= m) return;
+  int64_t r = __ldg(idx + i);
+  RowVec<D> v;
+  v.load(table + (size_t)r * D, lane);
+  v.store(out + (size_t)i * D, lane);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_gather_add_rows(const float* __restrict__ a, const int64_t* __restrict__ ia,
+                                                         const float* __restrict__ b, const int64_t* __restrict__ ib, int64_t m, int relu,
+                                                         float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= m) return;
+  RowVec<D> va, vb;
+  va.load(a + (size_t)__ldg(ia + i) * D, lane);
+  vb.load(b + (size_t)__ldg(ib + i) * D, lane);
+  va.add(vb);
+  if (relu) {
+#pragma unroll
+    for (int k = 0; k < RowVec<D>::N; ++k) va.v[k] = fmaxf(va.v[k], 0.f);
+  }
+  va.store(out + (size_t)i * D, lane);
+}
+
+
+__global__ void k_scatter_values(const float* __restrict__ vals, const int64_t* __restrict__ idx, int64_t m, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[idx[i]] = vals[i];
+}
+__global__ void k_gather_values(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t m, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] = src[idx[i]];
+}
+}  // namespace
+
+extern "C" int b2g_scatter_values(const float* vals, const int64_t* idx, int64_t m, float* out, void* stream_) {
+  B2G_CHECK_ARG(m >= 0 && (m == 0 || (vals && idx && out)), "scatter_values: bad args");
+  if (m == 0) return B2G_OK;
+  k_scatter_values<<<(unsigned)ceil_div(m, 256), 256, 0, (cudaStream_t)stream_>>>(vals, idx, m, out);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_gather_values(const float* src, const int64_t* idx, int64_t m, float* out, void* stream_) {
+  B2G_CHECK_ARG(m >= 0 && (m == 0 || (src && idx && out)), "gather_values: bad args");
+  if (m == 0) return B2G_OK;
+  k_gather_values<<<(unsigned)ceil_div(m, 256), 256, 0, (cudaStream_t)stream_>>>(src, idx, m, out);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_rows, int d, float* out, int accumulate,
+                                 void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(h_rels && n_rels >= 1 && n_rels <= 4 && n_rows >= 0 && out, "gather_reduce: bad args (n_rels=%d)", n_rels);
+  B2G_CHECK_ARG(aligned16(out), "gather_reduce: out not 16-byte aligned");
+  if (n_rows == 0) return B2G_OK;
+  RelPack pack{};
+  for (int k = 0; k < n_rels; ++k) {
+    B2G_CHECK_ARG(h_rels[k].rowptr && h_rels[k].x && aligned16(h_rels[k].x), "gather_reduce: relation %d has null/unaligned pointers", k);
+    pack.r[k] = h_rels[k];
+  }
+  unsigned grid = (unsigned)ceil_div(n_rows, 8);
+  DISPATCH_D(d, (k_gather_reduce<D><<<grid, 256, 0, st>>>(pack, n_rels, n_rows, out, accumulate)));
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_gather_reduce_chunked(const b2g_rel_t* h_rel, const int32_t* item_row, const int32_t* item_start,
+                                         const int32_t* row_item_ptr, int64_t n_items, int32_t chunk, int64_t n_rows, int d,
+                                         float* out, int accumulate, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(h_rel && h_rel->rowptr && h_rel->x && item_row && item_start && row_item_ptr && out && chunk > 0,
+                "gather_reduce_chunked: null pointer");
+  B2G_CHECK_ARG(aligned16(out) && aligned16(h_rel->x) && aligned16(ws), "gather_reduce_chunked: unaligned pointer");
+  if (n_rows == 0) return B2G_OK;
+  if (ws_bytes < (size_t)n_items * d * sizeof(float)) {
+    set_error("gather_reduce_chunked: workspace too small (%zu < %zu)", ws_bytes, (size_t)n_items * d * sizeof(float));
+    return B2G_EWS;
+  }
+  b2g_rel_t rel = *h_rel;
+  float* partial = (float*)ws;
+  unsigned g1 = (unsigned)ceil_div(n_items, 8), g2 = (unsigned)ceil_div(n_rows, 8);
+  DISPATCH_D(d, (k_chunk_partial<D><<<g1, 256, 0, st>>>(rel, item_row, item_start, n_items, chunk, partial)));
+  B2G_LAUNCH_CHECK();
+  DISPATCH_D(d, (k_chunk_final<D><<<g2, 256, 0, st>>>(partial, row_item_ptr, rel.row_scale, n_rows, out, accumulate)));
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_gather_rows(const float* table, const int64_t* idx, int64_t m, int64_t n_table, int d, float* out, void* stream_) {
+  (void)n_table;
+  B2G_CHECK_ARG(m >= 0 && (m == 0 || (table && idx && out)), "gather_rows: null pointer");
+  if (m == 0) return B2G_OK;
+  B2G_CHECK_ARG(aligned16(table) && aligned16(out), "gather_rows: unaligned pointer");
+  unsigned grid = (unsigned)ceil_div(m, 8);
+  DISPATCH_D(d, (k_gather_rows<D><<<grid, 256, 0, (cudaStream_t)stream_>>>(table, idx, m, out)));
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_gather_add_rows(const float* a, const int64_t* ia, const float* b, const int64_t* ib, int64_t m, int d, int relu,
+                                   float* out, void* stream_) {
+  B2G_CHECK_ARG(m >= 0 && (m == 0 || (a && ia && b && ib && out)), "gather_add_rows: null pointer");
+  if (m == 0) return B2G_OK;
+  B2G_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(out), "gather_add_rows: unaligned pointer");
+  unsigned grid = (unsigned)ceil_div(m, 8);
+  DISPATCH_D(d, (k_gather_add_rows<D><<<grid, 256, 0, (cudaStream_t)stream_>>>(a, ia, b, ib, m, relu, out)));
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}

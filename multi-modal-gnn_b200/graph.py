@@ -1,0 +1,176 @@
+"""Device-resident graph structure: per-relation CSR in both directions, degrees, the gate's degree
+vector, and CSR views of (patient, lab) prediction pairs.
+
+Input contract = what /root/reference/src/graph_build.py:148-261 emits: ``edge_index [2,E] int64`` COO per
+edge type.  The structure is built once per graph object (the graph is static for a whole run, SURVEY.md
+note N5) by libb2g's radix-sort CSR builder and cached.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+EdgeType = Tuple[str, str, str]
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.B2GError(f"{what} must live on a CUDA device (got {t.device}); this package has no CPU path")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_WS: Dict[int, torch.Tensor] = {}
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Grow-only scratch buffer per device (all library calls are stream-ordered on the current stream)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    buf = _WS.get(idx)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=torch.device("cuda", idx))
+        _WS[idx] = buf
+    return buf
+
+
+class CSR:
+    """rows -> sorted (stable) list of neighbour ids.  ``long_rows`` switches the reducer to the chunked
+    two-phase kernel (type-destination rows own up to millions of neighbours)."""
+
+    def __init__(self, key: torch.Tensor, val: torch.Tensor, n_rows: int, n_vals: int, col_is_eid: bool = False):
+        _require_cuda(key, "edge_index")
+        lib = _lib.load()
+        dev = key.device
+        key = key.contiguous()
+        val = val.contiguous()
+        if key.dtype != torch.int64 or val.dtype != torch.int64:
+            key, val = key.long(), val.long()
+        e = int(key.numel())
+        self.n_rows, self.n_vals, self.n_edges = int(n_rows), int(n_vals), e
+        self.rowptr = torch.empty(self.n_rows + 1, dtype=torch.int32, device=dev)
+        self.col = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+        self.eid = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+        ws_bytes = lib.b2g_csr_build_ws_bytes(e, self.n_rows)
+        ws = workspace(ws_bytes, dev)
+        _lib.check(lib.b2g_csr_build(key.data_ptr(), val.data_ptr(), e, self.n_rows, self.n_vals, self.rowptr.data_ptr(),
+                                     self.col.data_ptr(), self.eid.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                   "b2g_csr_build")
+        if col_is_eid:
+            self.col = self.eid
+        self.deg = torch.empty(self.n_rows, dtype=torch.int64, device=dev)
+        self.inv_deg = torch.empty(self.n_rows, dtype=torch.float32, device=dev)
+        _lib.check(lib.b2g_csr_degrees(self.rowptr.data_ptr(), self.n_rows, self.deg.data_ptr(), self.inv_deg.data_ptr(),
+                                       _stream()), "b2g_csr_degrees")
+        # long-row decomposition
+        max_deg = int(self.deg.max().item()) if self.n_rows > 0 and e > 0 else 0
+        self.max_deg = max_deg
+        self.long_rows = max_deg > 1024
+        self.chunk = 0
+        self.n_items = 0
+        self.item_row = self.item_start = self.row_item_ptr = None
+        if self.long_rows:
+            chunk = 32
+            while chunk < 512 and e // (chunk * 2) >= 16384:
+                chunk *= 2
+            self.chunk = chunk
+            self.row_item_ptr = torch.empty(self.n_rows + 1, dtype=torch.int32, device=dev)
+            n_items = ctypes.c_int64(0)
+            wsb = lib.b2g_csr_chunk_ws_bytes(self.n_rows)
+            ws = workspace(wsb, dev)
+            _lib.check(lib.b2g_csr_chunk_count(self.rowptr.data_ptr(), self.n_rows, chunk, self.row_item_ptr.data_ptr(),
+                                               ctypes.byref(n_items), ws.data_ptr(), ws.numel(), _stream()),
+                       "b2g_csr_chunk_count")
+            self.n_items = int(n_items.value)
+            self.item_row = torch.empty(self.n_items, dtype=torch.int32, device=dev)
+            self.item_start = torch.empty(self.n_items, dtype=torch.int32, device=dev)
+            _lib.check(lib.b2g_csr_chunk_fill(self.rowptr.data_ptr(), self.n_rows, chunk, self.row_item_ptr.data_ptr(),
+                                              self.item_row.data_ptr(), self.item_start.data_ptr(), _stream()),
+                       "b2g_csr_chunk_fill")
+
+
+class Relation:
+    """One edge type (src, rel, dst): CSR keyed by destination (forward aggregation) and by source
+    (transposed aggregation for the backward pass -- no float atomics)."""
+
+    def __init__(self, edge_type: EdgeType, edge_index: torch.Tensor, n_src: int, n_dst: int):
+        self.edge_type = edge_type
+        self.n_src, self.n_dst = int(n_src), int(n_dst)
+        self.n_edges = int(edge_index.shape[1])
+        self.by_dst = CSR(edge_index[1], edge_index[0], n_dst, n_src)
+        self.by_src = CSR(edge_index[0], edge_index[1], n_src, n_dst)
+
+    @property
+    def inv_deg_dst(self):
+        return self.by_dst.inv_deg
+
+
+class GraphIndex:
+    """All relations of one heterogeneous graph + node counts."""
+
+    def __init__(self, data):
+        self.node_counts = {nt: int(data[nt].num_nodes) for nt in data.node_types}
+        self.relations: Dict[EdgeType, Relation] = {}
+        self._ptrs = {}
+        for et, ei in data.edge_index_dict.items():
+            et = tuple(et)
+            src, _, dst = et
+            _require_cuda(ei, f"edge_index of {et}")
+            if ei.dim() != 2 or ei.shape[0] != 2:
+                raise ValueError(f"edge_index of {et} must have shape [2, E], got {tuple(ei.shape)}")
+            try:
+                self.relations[et] = Relation(et, ei, self.node_counts[src], self.node_counts[dst])
+            except _lib.B2GError as exc:
+                if "out of range" in str(exc):
+                    raise ValueError(f"edge_index of {et} has endpoints outside the node range") from exc
+                raise
+            self._ptrs[et] = (ei.data_ptr(), int(ei.shape[1]))
+        lab_rel = self.relations.get(("patient", "has_lab", "lab"))
+        # model.py:297-298: torch.bincount(has_lab.edge_index[0], minlength=N_patient) == row degrees of the by-source CSR
+        self.patient_lab_degree: Optional[torch.Tensor] = lab_rel.by_src.deg if lab_rel is not None else None
+
+    def matches(self, data) -> bool:
+        eid = data.edge_index_dict
+        if set(map(tuple, eid.keys())) != set(self._ptrs):
+            return False
+        return all(self._ptrs[tuple(k)] == (v.data_ptr(), int(v.shape[1])) for k, v in eid.items())
+
+
+_GRAPH_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_GRAPH_CACHE_STRONG: Dict[int, Tuple[object, GraphIndex]] = {}
+
+
+def graph_index(data) -> GraphIndex:
+    """Cached GraphIndex for a HeteroData-like object (rebuilt if its edge tensors were replaced)."""
+    try:
+        gi = _GRAPH_CACHE.get(data)
+    except TypeError:
+        ent = _GRAPH_CACHE_STRONG.get(id(data))
+        gi = ent[1] if ent is not None and ent[0] is data else None
+    if gi is not None and gi.matches(data):
+        return gi
+    gi = GraphIndex(data)
+    try:
+        _GRAPH_CACHE[data] = gi
+    except TypeError:
+        _GRAPH_CACHE_STRONG[id(data)] = (data, gi)
+    return gi
+
+
+class PairIndex:
+    """CSR views of a list of (patient, lab) prediction pairs, used by the decoder's backward to turn the
+    per-pair gradients into per-patient / per-lab sums without atomics (replaces autograd's
+    ``index_put_(accumulate=True)`` behind model.py:305-309)."""
+
+    def __init__(self, patient_idx: torch.Tensor, lab_idx: torch.Tensor, n_patient: int, n_lab: int):
+        self.m = int(patient_idx.numel())
+        self.patient_idx = patient_idx.contiguous()
+        self.lab_idx = lab_idx.contiguous()
+        self.by_patient = CSR(self.patient_idx, self.patient_idx, n_patient, n_patient, col_is_eid=True)
+        self.by_lab = CSR(self.lab_idx, self.lab_idx, n_lab, n_lab, col_is_eid=True)

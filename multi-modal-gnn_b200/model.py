@@ -1,0 +1,430 @@
+"""Drop-in replacement for the reference's ``src/model.py`` call surface:
+
+    build_model(config, metadata, patient_feature_dim) -> nn.Module
+    HeteroRGCN._init_embeddings / encode_nodes / forward / predict_lab_values
+    EdgeRegressionHead, compute_regression_loss
+
+Same parameter / buffer names and shapes as the reference (108 ``state_dict`` entries for the shipped
+config), so ``torch.optim.Adam``, ``torch.save`` and ``load_state_dict`` in the reference's ``train.py`` /
+``evaluate.py`` / ``inference.py`` keep working unchanged; all arithmetic runs in libb2g's sm_100a kernels
+(``ops.py``).  The ``nn.Linear`` / ``nn.BatchNorm1d`` / ``nn.Embedding`` objects below are parameter
+containers only -- their ``forward`` is never called.
+
+Reference behaviours kept on purpose (SURVEY.md section 3.1 notes):
+  N2  tables are created lazily at the first forward, i.e. after train.py built its optimizer -> they are
+      not optimised unless the caller creates them first (``_init_embeddings``);
+  N3  ``predict_lab_values`` encodes twice in training mode (two dropout draws, two running-stat updates of
+      the patient MLP's BatchNorms); with dropout == 0 the two passes are identical, so one pass is computed
+      and the second running-stat update is applied analytically;
+  N4  edge_attr is never a message weight;  N8  the last layer's diagnosis / medication outputs are computed
+      (their BN running stats move) but receive no gradient.
+Reference defect fixed on purpose: N1 -- lazily created tables are placed on the module's device.
+"""
+from __future__ import annotations
+
+import logging
+import re
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .graph import GraphIndex, PairIndex, graph_index, _stream
+
+EdgeType = Tuple[str, str, str]
+
+
+class _DropoutStreams:
+    """Per-call dropout bookkeeping: one 64-bit seed drawn from torch's CPU generator (so
+    ``torch.manual_seed`` makes runs repeatable) and a running stream id, one per dropout site."""
+
+    def __init__(self, active: bool):
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if active else 0
+        self.next_id = 0
+        self.log: List[Tuple[str, int]] = []
+
+    def take(self, tag: str = "") -> int:
+        sid = self.next_id
+        self.next_id += 1
+        self.log.append((tag, sid))
+        return sid
+
+
+def _bn_act_drop(x, bn: Optional[nn.BatchNorm1d], training: bool, act: int, p: float, streams: _DropoutStreams, tag: str):
+    sid = streams.take(tag) if (training and p > 0) else 0
+    if bn is None:
+        return ops.ActDropFn.apply(x, act, p, streams.seed, sid, training)
+    if training and bn.track_running_stats:
+        bn.num_batches_tracked += 1
+    return ops.BNActDropFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, act, p, streams.seed, sid,
+                                 bn.eps, bn.momentum if bn.momentum is not None else 0.1)
+
+
+class EdgeRegressionHead(nn.Module):
+    """Linear(2d,64)-ReLU-Dropout-Linear(64,32)-ReLU-Dropout-Linear(32,1)  (model.py:342-396)."""
+
+    def __init__(self, input_dim: int, hidden_dims: list = [64, 32], output_dim: int = 1, dropout: float = 0.2):
+        super().__init__()
+        layers = []
+        prev = input_dim
+        for h in hidden_dims:
+            layers += [nn.Linear(prev, h), nn.ReLU(), nn.Dropout(dropout)]
+            prev = h
+        layers.append(nn.Linear(prev, output_dim))
+        self.mlp = nn.Sequential(*layers)
+        self.dropout_p = float(dropout)
+
+    def _linears(self):
+        return [m for m in self.mlp if isinstance(m, nn.Linear)]
+
+    def _tail(self, h, linears, streams, tag, relu_done=False):
+        """everything after the first Linear: ReLU-Dropout-(Linear-ReLU-Dropout)*-Linear; ``relu_done`` says
+        the first ReLU was already fused into the producer of ``h``."""
+        training = self.training
+        drop = training and self.dropout_p > 0
+        for i, lin in enumerate(linears):
+            need_relu = not (relu_done and i == 0)
+            if need_relu or drop:
+                sid = streams.take(f"{tag}.drop{i}") if drop else 0
+                h = ops.ReluDropoutFn.apply(h, int(need_relu), self.dropout_p, streams.seed, sid, training)
+            h = ops.linear(h, lin.weight, lin.bias)
+        return h
+
+    def forward(self, edge_embeds: torch.Tensor, _streams: Optional[_DropoutStreams] = None) -> torch.Tensor:
+        """edge_embeds [m, input_dim] -> [m, output_dim]  (model.py:388-396)."""
+        streams = _streams or _DropoutStreams(self.training and self.dropout_p > 0)
+        lins = self._linears()
+        h = ops.linear(edge_embeds, lins[0].weight, lins[0].bias)
+        return self._tail(h, lins[1:], streams, "head")
+
+    def forward_pairs(self, h_p: torch.Tensor, h_l: torch.Tensor, pairs: PairIndex, streams: _DropoutStreams, tag: str):
+        """Same function of cat([h_p[pi], h_l[li]], 1) (model.py:319-333) with the first layer factorised per
+        node: U = h_p W[:, :d]^T on patients, V = h_l W[:, d:]^T + b on labs, z = relu(U[pi] + V[li])."""
+        lins = self._linears()
+        if len(lins) < 2:
+            raise _lib.B2GError("EdgeRegressionHead needs at least one hidden layer")
+        d = h_p.shape[1]
+        w0 = lins[0].weight
+        u = ops.linear(h_p, w0[:, :d].contiguous(), None)
+        v = ops.linear(h_l, w0[:, d:].contiguous(), lins[0].bias)
+        z = ops.PairAddReluFn.apply(u, v, pairs)
+        out = self._tail(z, lins[1:], streams, tag, relu_done=True)
+        return out.squeeze(-1)
+
+
+class _SAGEParams(nn.Module):
+    """Parameter container with PyG SAGEConv's names: lin_l (bias) on the aggregated neighbours, lin_r (no
+    bias) on the destination's own features (PyG sage_conv.py; param count pinned by SURVEY.md KA-1)."""
+
+    def __init__(self, d_in: int, d_out: int):
+        super().__init__()
+        self.lin_l = nn.Linear(d_in, d_out, bias=True)
+        self.lin_r = nn.Linear(d_in, d_out, bias=False)
+
+
+class _HeteroConvParams(nn.Module):
+    def __init__(self, edge_types, d: int):
+        super().__init__()
+        self.convs = nn.ModuleDict({"__".join(et): _SAGEParams(d, d) for et in edge_types})
+
+
+_PYG24_KEY = re.compile(r"<([^<>]+?)___([^<>]+?)___([^<>]+?)>")
+
+
+class HeteroRGCN(nn.Module):
+    """Relational SAGE network of the reference (model.py:33-335) on libb2g kernels."""
+
+    def __init__(self, metadata: Tuple, hidden_dim: int = 128, num_layers: int = 2, dropout: float = 0.2,
+                 patient_feature_dim: int = None, use_batch_norm: bool = True, activation: str = "relu"):
+        super().__init__()
+        if activation not in ("relu", "elu", "leaky_relu"):
+            raise ValueError(f"Unknown activation: {activation}")
+        if hidden_dim not in (32, 64, 128, 256):
+            raise ValueError(f"hidden_dim must be one of 32/64/128/256 for the sm_100a kernels, got {hidden_dim}")
+        self.hidden_dim = hidden_dim
+        self.num_layers = num_layers
+        self.dropout = dropout
+        self.use_batch_norm = use_batch_norm
+        self.activation_name = activation
+        self._act = ops.ACT_CODES[activation]
+        node_types, edge_types = metadata
+        self._node_types = list(node_types)
+        self._edge_types = [tuple(et) for et in edge_types]
+
+        self.embeddings = nn.ModuleDict()
+        self.embedding_dims = {}
+        self.patient_transform = nn.Sequential(
+            nn.Linear(hidden_dim, hidden_dim), nn.BatchNorm1d(hidden_dim), nn.ReLU(), nn.Dropout(dropout),
+            nn.Linear(hidden_dim, hidden_dim), nn.BatchNorm1d(hidden_dim), nn.ReLU(), nn.Dropout(dropout),
+            nn.Linear(hidden_dim, hidden_dim))
+        self.convs = nn.ModuleList([_HeteroConvParams(self._edge_types, hidden_dim) for _ in range(num_layers)])
+        self.batch_norms = (nn.ModuleList([nn.ModuleDict({nt: nn.BatchNorm1d(hidden_dim) for nt in node_types})
+                                           for _ in range(num_layers)]) if use_batch_norm else None)
+        self.edge_predictor = EdgeRegressionHead(2 * hidden_dim, [64, 32], 1, dropout)
+        self.tabular_mlp = EdgeRegressionHead(2 * hidden_dim, [64, 32], 1, dropout)
+        self.degree_threshold = 6
+        self._pair_plans: "OrderedDict[int, _PairPlan]" = OrderedDict()
+        self._last_streams: Optional[_DropoutStreams] = None
+        self._register_load_state_dict_pre_hook(self._rename_pyg24_keys)
+        logging.info(f"Initialized HeteroRGCN with hidden_dim={hidden_dim}, num_layers={num_layers}")
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _rename_pyg24_keys(state_dict, prefix, *args):
+        """Accept PyG >= 2.4 conv keys ('<src___rel___dst>') as well as the 2.3 form ('src__rel__dst')."""
+        for k in list(state_dict.keys()):
+            nk = _PYG24_KEY.sub(lambda m: "__".join(m.groups()), k)
+            if nk != k:
+                state_dict[nk] = state_dict.pop(k)
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def _init_embeddings(self, data):
+        """model.py:180-204 -- idempotent; tables live on the module's device (fixes reference note N1)."""
+        dev = self._device()
+        for nt in data.node_types:
+            if nt not in self.embeddings:
+                n = int(data[nt].num_nodes)
+                emb = nn.Embedding(n, self.hidden_dim)
+                nn.init.xavier_uniform_(emb.weight)
+                self.embeddings[nt] = emb.to(dev)
+                self.embedding_dims[nt] = n
+                logging.info(f"Created embedding for {nt}: {n} nodes")
+
+    # ------------------------------------------------------------------------------------------
+    def _encode(self, node_types, streams: _DropoutStreams, tag: str) -> Dict[str, torch.Tensor]:
+        """model.py:206-234.  embedding(arange(N)) is the table itself; patient rows go through
+        Linear-BN-ReLU-Dropout x2, Linear, row L2 normalisation."""
+        training = self.training
+        x = {nt: self.embeddings[nt].weight for nt in node_types}
+        if "patient" in x:
+            pt = self.patient_transform
+            h = ops.linear(x["patient"], pt[0].weight, pt[0].bias)
+            h = _bn_act_drop(h, pt[1], training, 1, self.dropout, streams, tag + ".drop0")
+            h = ops.linear(h, pt[4].weight, pt[4].bias)
+            h = _bn_act_drop(h, pt[5], training, 1, self.dropout, streams, tag + ".drop1")
+            h = ops.linear(h, pt[8].weight, pt[8].bias)
+            x["patient"] = ops.L2NormFn.apply(h, 1e-12)
+        return x
+
+    def _layer(self, layer: int, x: Dict[str, torch.Tensor], gi: GraphIndex) -> Dict[str, torch.Tensor]:
+        """HeteroConv({et: SAGEConv(mean)}, aggr='sum') (model.py:125-131,256): per destination type one fused
+        SageDstFn (see ops.py)."""
+        convs = self.convs[layer].convs
+        by_dst: "OrderedDict[str, list]" = OrderedDict()
+        for et in self._edge_types:
+            if et in gi.relations and et[0] in x and et[2] in x:
+                by_dst.setdefault(et[2], []).append(et)
+        out = {}
+        for dst, ets in by_dst.items():
+            w_root = b_root = None
+            small_rels, ys, aggs, wls = [], [], [], []
+            for et in ets:
+                conv = convs["__".join(et)]
+                w_root = conv.lin_r.weight if w_root is None else w_root + conv.lin_r.weight
+                b_root = conv.lin_l.bias if b_root is None else b_root + conv.lin_l.bias
+                rel = gi.relations[et]
+                if rel.n_src < rel.n_dst:          # few sources: transform them first, then aggregate
+                    small_rels.append(rel)
+                    ys.append(ops.linear(x[et[0]], conv.lin_l.weight, None))
+                else:                              # many sources: aggregate first, then transform
+                    aggs.append(ops.MeanAggFn.apply(x[et[0]], rel))
+                    wls.append(conv.lin_l.weight)
+            out[dst] = ops.SageDstFn.apply(x[dst], w_root, b_root, tuple(small_rels), len(aggs), *ys, *aggs, *wls)
+        return out
+
+    def _gnn(self, x: Dict[str, torch.Tensor], gi: GraphIndex, streams: _DropoutStreams) -> Dict[str, torch.Tensor]:
+        training = self.training
+        for layer in range(self.num_layers):
+            x = self._layer(layer, x, gi)
+            p = self.dropout if layer < self.num_layers - 1 else 0.0
+            nx = {}
+            for nt, v in x.items():
+                bn = self.batch_norms[layer][nt] if self.use_batch_norm else None
+                nx[nt] = _bn_act_drop(v, bn, training, self._act, p, streams, f"fwd.l{layer}.{nt}")
+            x = nx
+        return x
+
+    def _streams(self) -> _DropoutStreams:
+        s = _DropoutStreams(self.training and self.dropout > 0)
+        self._last_streams = s
+        return s
+
+    def _check_device(self):
+        if self._device().type != "cuda":
+            raise _lib.B2GError("HeteroRGCN runs only on a CUDA device (B200); call .to('cuda') first -- there is no CPU path")
+
+    # ------------------------------------------------------------------------------------------
+    def encode_nodes(self, data) -> Dict[str, torch.Tensor]:
+        """model.py:206-234 (public: advanced_visualizations.py:285)."""
+        self._check_device()
+        if len(self.embeddings) == 0:
+            self._init_embeddings(data)
+        return self._encode(list(data.node_types), self._streams(), "enc")
+
+    def forward(self, data) -> Dict[str, torch.Tensor]:
+        """model.py:236-271."""
+        self._check_device()
+        if len(self.embeddings) == 0:
+            self._init_embeddings(data)
+        gi = graph_index(data)
+        streams = self._streams()
+        x = self._encode(list(data.node_types), streams, "fwd.enc")
+        return self._gnn(x, gi, streams)
+
+    def predict_lab_values(self, data, patient_indices: torch.Tensor, lab_indices: torch.Tensor) -> torch.Tensor:
+        """model.py:273-335: degree-gated edge regression for (patient, lab) pairs."""
+        self._check_device()
+        if len(self.embeddings) == 0:
+            self._init_embeddings(data)
+        if not patient_indices.is_cuda or not lab_indices.is_cuda:
+            raise _lib.B2GError("patient_indices / lab_indices must be CUDA tensors")
+        gi = graph_index(data)
+        node_types = list(data.node_types)
+        streams = self._streams()
+        training = self.training
+
+        if training and self.dropout > 0:
+            init = self._encode(node_types, streams, "init.enc")         # model.py:294
+            x0 = self._encode(node_types, streams, "fwd.enc")            # model.py:251 (fresh masks, N3)
+        else:
+            bns = [self.patient_transform[1], self.patient_transform[5]]
+            before = [(b.running_mean.clone(), b.running_var.clone()) for b in bns] if training else None
+            init = self._encode(node_types, streams, "enc")
+            x0 = init
+            if training:     # second, identical running-stat update of the reference's second encode (N3)
+                with torch.no_grad():
+                    for b, (rm0, rv0) in zip(bns, before):
+                        mom = b.momentum if b.momentum is not None else 0.1
+                        # r1 = (1-m) r0 + m s  ->  r2 = (1-m) r1 + m s = (2-m) r1 - (1-m) r0
+                        b.running_mean.mul_(2 - mom).sub_(rm0, alpha=1 - mom)
+                        b.running_var.mul_(2 - mom).sub_(rv0, alpha=1 - mom)
+                        b.num_batches_tracked += 1
+        x = self._gnn(x0, gi, streams)
+
+        plan = self._pair_plan(gi, patient_indices, lab_indices)
+        outs = []
+        if plan.low is not None:
+            outs.append(self.tabular_mlp.forward_pairs(init["patient"], init["lab"], plan.low, streams, "tabular_mlp"))
+        if plan.high is not None:
+            outs.append(self.edge_predictor.forward_pairs(x["patient"], x["lab"], plan.high, streams, "edge_predictor"))
+        if plan.m == 0:
+            return torch.zeros(0, dtype=torch.float32, device=patient_indices.device)
+        if plan.idx_low is None:      # a single head covers every pair, already in caller order
+            return outs[0]
+        return _AssembleFn.apply(outs[0], outs[1], plan.idx_low, plan.idx_high, plan.m)
+
+    # ------------------------------------------------------------------------------------------
+    def _pair_plan(self, gi: GraphIndex, pi: torch.Tensor, li: torch.Tensor) -> "_PairPlan":
+        for key, plan in self._pair_plans.items():
+            if plan.gi is gi and plan.same_pairs(pi, li):
+                self._pair_plans.move_to_end(key)
+                return plan
+        plan = _PairPlan(gi, pi, li, self.degree_threshold)
+        self._pair_plans[id(plan)] = plan
+        while len(self._pair_plans) > 4:
+            self._pair_plans.popitem(last=False)
+        return plan
+
+
+class _PairPlan:
+    """Gate + index structures for one list of (patient, lab) pairs (model.py:305-333).  Cached per model:
+    train.py re-creates equal index tensors every epoch, so lookups compare content, not identity."""
+
+    def __init__(self, gi: GraphIndex, pi: torch.Tensor, li: torch.Tensor, threshold: int):
+        lib = _lib.load()
+        self.gi = gi
+        self.pi, self.li = pi, li
+        self.versions = (pi._version, li._version)
+        self.m = int(pi.numel())
+        n_p, n_l = gi.node_counts["patient"], gi.node_counts["lab"]
+        pi64 = pi.contiguous() if pi.dtype == torch.int64 else pi.long()
+        li64 = li.contiguous() if li.dtype == torch.int64 else li.long()
+        self.low = self.high = self.idx_low = self.idx_high = None
+        self.low_mask = torch.zeros(self.m, dtype=torch.uint8, device=pi.device)
+        if self.m == 0:
+            return
+        if gi.patient_lab_degree is None:
+            raise _lib.B2GError("graph has no ('patient','has_lab','lab') relation: cannot compute the degree gate")
+        _lib.check(lib.b2g_degree_gate(gi.patient_lab_degree.data_ptr(), pi64.data_ptr(), self.m, int(threshold),
+                                       self.low_mask.data_ptr(), _stream()), "b2g_degree_gate")
+        n_low = int(self.low_mask.sum().item())
+        if n_low == 0:
+            self.high = PairIndex(pi64, li64, n_p, n_l)
+        elif n_low == self.m:
+            self.low = PairIndex(pi64, li64, n_p, n_l)
+        else:
+            mask = self.low_mask.bool()
+            self.idx_low = mask.nonzero().squeeze(1)
+            self.idx_high = (~mask).nonzero().squeeze(1)
+            self.low = PairIndex(pi64[self.idx_low], li64[self.idx_low], n_p, n_l)
+            self.high = PairIndex(pi64[self.idx_high], li64[self.idx_high], n_p, n_l)
+
+    def same_pairs(self, pi, li) -> bool:
+        if pi is self.pi and li is self.li and (pi._version, li._version) == self.versions:
+            return True
+        if pi.numel() != self.m or pi.dtype != self.pi.dtype or li.dtype != self.li.dtype or pi.device != self.pi.device:
+            return False
+        if (self.pi._version, self.li._version) != self.versions:
+            return False
+        return bool(torch.equal(pi, self.pi)) and bool(torch.equal(li, self.li))
+
+
+class _AssembleFn(torch.autograd.Function):
+    """predictions[low] = tabular head, predictions[~low] = GNN head (model.py:317-333)."""
+
+    @staticmethod
+    def forward(ctx, out_low, out_high, idx_low, idx_high, m):
+        lib = _lib.load()
+        out_low, out_high = out_low.contiguous(), out_high.contiguous()
+        pred = torch.empty(m, dtype=torch.float32, device=out_low.device)
+        _lib.check(lib.b2g_scatter_values(out_low.data_ptr(), idx_low.data_ptr(), idx_low.numel(), pred.data_ptr(), _stream()),
+                   "b2g_scatter_values")
+        _lib.check(lib.b2g_scatter_values(out_high.data_ptr(), idx_high.data_ptr(), idx_high.numel(), pred.data_ptr(), _stream()),
+                   "b2g_scatter_values")
+        ctx.idx = (idx_low, idx_high)
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        lib = _lib.load()
+        idx_low, idx_high = ctx.idx
+        dpred = dpred.contiguous()
+        dl = torch.empty(idx_low.numel(), dtype=torch.float32, device=dpred.device)
+        dh = torch.empty(idx_high.numel(), dtype=torch.float32, device=dpred.device)
+        _lib.check(lib.b2g_gather_values(dpred.data_ptr(), idx_low.data_ptr(), idx_low.numel(), dl.data_ptr(), _stream()),
+                   "b2g_gather_values")
+        _lib.check(lib.b2g_gather_values(dpred.data_ptr(), idx_high.data_ptr(), idx_high.numel(), dh.data_ptr(), _stream()),
+                   "b2g_gather_values")
+        return dl, dh, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------
+def build_model(config: Dict, metadata: Tuple, patient_feature_dim: int):
+    """model.py:523-572.  Reads exactly config['model'][architecture, hidden_dim, num_layers, dropout,
+    use_batch_norm, activation]; constructible before the graph is seen."""
+    mc = config["model"]
+    arch = mc["architecture"]
+    if arch == "RGCN":
+        model = HeteroRGCN(metadata=metadata, hidden_dim=mc["hidden_dim"], num_layers=mc["num_layers"], dropout=mc["dropout"],
+                           patient_feature_dim=patient_feature_dim, use_batch_norm=mc["use_batch_norm"],
+                           activation=mc["activation"])
+        logging.info("Built HeteroRGCN model")
+    elif arch == "HGT":
+        raise NotImplementedError("HGT is unreachable in the reference's shipped configuration (needs patient.x, which "
+                                  "graph_build.py no longer sets) and is outside the accelerated hot path")
+    else:
+        raise ValueError(f"Unknown architecture: {arch}")
+    n = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    logging.info(f"Model has {n:,} trainable parameters")
+    return model
+
+
+def compute_regression_loss(predictions: torch.Tensor, targets: torch.Tensor, loss_type: str = "mae") -> torch.Tensor:
+    """model.py:579-612: unweighted l1 / mse / huber mean, one fused deterministic reduction."""
+    if loss_type not in ops.LOSS_KINDS:
+        raise ValueError(f"Unknown loss type: {loss_type}")
+    return ops.weighted_loss(predictions, targets, None, None, None, loss_type)

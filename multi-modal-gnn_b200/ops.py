@@ -1,0 +1,503 @@
+"""autograd.Function wrappers over libb2g's C ABI.  PyTorch here is plumbing only: device memory, the
+current CUDA stream and the autograd tape; every arithmetic kernel is ours (csrc/*.cu).
+
+Each Function cites the reference expression it replaces.  There is no CPU implementation: passing a
+CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .graph import CSR, PairIndex, Relation, workspace, _stream
+
+ACT_CODES = {"none": 0, "relu": 1, "leaky_relu": 2, "elu": 3}
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.B2GError(f"{name} must be a CUDA tensor (got {t.device}); this package has no CPU path")
+    if t.dtype != torch.float32:
+        raise _lib.B2GError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+# Optional per-call profiler: when PROFILE is a list, every library call is bracketed by CUDA events on the
+# launching (current) stream and appended as (name, start, end, algorithmic_bytes, flops).  bench.py uses it for
+# one instrumented step to find the dominant kernel and its live duration.
+PROFILE: Optional[list] = None
+_NEXT_COST = [0, 0]
+
+
+def cost(nbytes: int = 0, flops: int = 0):
+    """Declare the algorithmic bytes / flops of the next library call (read only when profiling)."""
+    _NEXT_COST[0], _NEXT_COST[1] = int(nbytes), int(flops)
+
+
+def _run(name, fn, *args):
+    prof = PROFILE
+    if prof is None:
+        rc = fn(*args)
+    else:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        prof.append((name, s, e, _NEXT_COST[0], _NEXT_COST[1]))
+        _NEXT_COST[0] = _NEXT_COST[1] = 0
+    if rc != 0:
+        _lib.check(rc, name)
+
+
+# --------------------------------------------------------------------------------------------------
+# raw (non-differentiable) kernel calls
+# --------------------------------------------------------------------------------------------------
+def linear_fwd_(x, w, b, y, accumulate=False):
+    lib = _lib.load()
+    m, k = x.shape
+    n = w.shape[0]
+    cost(4 * (m * k + n * k + m * n * (2 if accumulate else 1)), 2 * m * n * k)
+    _run("b2g_linear_fwd", lib.b2g_linear_fwd, x.data_ptr(), w.data_ptr(), _ptr(b), m, n, k, y.data_ptr(), int(accumulate), _stream())
+    return y
+
+
+def linear_bwd_input_(dy, w, dx, accumulate=False):
+    lib = _lib.load()
+    m, n = dy.shape
+    k = w.shape[1]
+    cost(4 * (m * n + n * k + m * k * (2 if accumulate else 1)), 2 * m * n * k)
+    _run("b2g_linear_bwd_input", lib.b2g_linear_bwd_input, dy.data_ptr(), w.data_ptr(), m, n, k, dx.data_ptr(), int(accumulate), _stream())
+    return dx
+
+
+def linear_bwd_weight_(dy, x, dw, db):
+    lib = _lib.load()
+    m, n = dy.shape
+    k = x.shape[1]
+    nb = lib.b2g_linear_bwd_weight_ws_bytes(m, n, k)
+    ws = workspace(nb, dy.device)
+    cost(4 * (m * n + m * k + n * k), 2 * m * n * k)
+    _run("b2g_linear_bwd_weight", lib.b2g_linear_bwd_weight, dy.data_ptr(), x.data_ptr(), m, n, k, dw.data_ptr(), _ptr(db), ws.data_ptr(),
+                                         ws.numel(), _stream())
+
+
+def gather_reduce_(csrs: Sequence[CSR], xs: Sequence[torch.Tensor], row_scales, col_scales, out: torch.Tensor,
+                   accumulate: bool):
+    """out[r] (+)= sum_k row_scale_k[r] * sum_{j in row r} col_scale_k[col_j] * x_k[col_j].  Short-row CSRs are
+    fused into one launch (<= 4 relations); long-row CSRs go through the chunked two-phase reducer."""
+    lib = _lib.load()
+    d = out.shape[1]
+    n_rows = out.shape[0]
+    short = [i for i, c in enumerate(csrs) if not c.long_rows]
+    long_ = [i for i, c in enumerate(csrs) if c.long_rows]
+    acc = bool(accumulate)
+    for s0 in range(0, len(short), 4):
+        grp = short[s0:s0 + 4]
+        arr = (_lib.RelT * len(grp))()
+        for j, i in enumerate(grp):
+            c = csrs[i]
+            assert c.n_rows == n_rows
+            arr[j].rowptr, arr[j].col, arr[j].x = c.rowptr.data_ptr(), c.col.data_ptr(), xs[i].data_ptr()
+            arr[j].row_scale = _ptr(row_scales[i])
+            arr[j].col_scale = _ptr(col_scales[i])
+        # algorithmic bytes: CSR indices once + output rows once (+ read when accumulating) + source tables once
+        cost(sum(4 * (csrs[i].n_edges + csrs[i].n_rows + 1) + 4 * d * min(csrs[i].n_vals, csrs[i].n_edges) for i in grp)
+             + 4 * n_rows * d * (2 if acc else 1), 2 * d * sum(csrs[i].n_edges for i in grp))
+        _run("b2g_gather_reduce", lib.b2g_gather_reduce, arr, len(grp), n_rows, d, out.data_ptr(), int(acc), _stream())
+        acc = True
+    for i in long_:
+        c = csrs[i]
+        assert c.n_rows == n_rows
+        rel = _lib.RelT()
+        rel.rowptr, rel.col, rel.x = c.rowptr.data_ptr(), c.col.data_ptr(), xs[i].data_ptr()
+        rel.row_scale = _ptr(row_scales[i])
+        rel.col_scale = _ptr(col_scales[i])
+        ws = workspace(c.n_items * d * 4, out.device)
+        cost(4 * (c.n_edges + c.n_rows + 1) + 4 * d * min(c.n_vals, c.n_edges) + 4 * n_rows * d * (2 if acc else 1),
+             2 * d * c.n_edges)
+        _run("b2g_gather_reduce_chunked", lib.b2g_gather_reduce_chunked, ctypes.byref(rel), c.item_row.data_ptr(), c.item_start.data_ptr(),
+                                                 c.row_item_ptr.data_ptr(), c.n_items, c.chunk, n_rows, d, out.data_ptr(),
+                                                 int(acc), ws.data_ptr(), ws.numel(), _stream())
+        acc = True
+    if not acc:          # no relation at all
+        out.zero_()
+    return out
+
+
+def dropout_mask(n: int, p: float, seed: int, stream_id: int, device) -> torch.Tensor:
+    """The keep mask (0 or 1/(1-p)) the kernels apply for (seed, stream_id) -- for replay on the CPU oracle."""
+    lib = _lib.load()
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    _run("b2g_dropout_mask", lib.b2g_dropout_mask, n, float(p), int(seed), int(stream_id), out.data_ptr(), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# differentiable ops
+# --------------------------------------------------------------------------------------------------
+class LinearFn(Function):
+    """y = x W^T + b   (nn.Linear; model.py:93-103,373-386 and SAGEConv.lin_l / lin_r)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = _f32(x, "x"), _f32(w, "weight")
+        b = None if b is None else _f32(b, "bias")
+        y = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+        linear_fwd_(x, w, b, y)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _f32(dy, "grad")
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            linear_bwd_input_(dy, w, dx)
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or need_b:
+            dw = torch.empty_like(w)
+            db = torch.empty(w.shape[0], dtype=torch.float32, device=w.device) if need_b else None
+            linear_bwd_weight_(dy, x, dw, db)
+        return dx, dw, db
+
+
+def linear(x, w, b=None):
+    return LinearFn.apply(x, w, b)
+
+
+class BNActDropFn(Function):
+    """dropout(act(batch_norm(x)))  -- nn.BatchNorm1d -> activation -> F.dropout (model.py:93-101,259-269).
+    Training mode uses batch statistics and updates the running buffers in place (momentum 0.1, unbiased
+    variance); eval mode uses the running buffers.  The dropout mask is regenerated from (seed, sid)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, act, p_drop, seed, sid, eps, momentum):
+        lib = _lib.load()
+        x, gamma, beta = _f32(x, "x"), _f32(gamma, "bn.weight"), _f32(beta, "bn.bias")
+        m, d = x.shape
+        dev = x.device
+        mean = torch.empty(d, dtype=torch.float32, device=dev)
+        rstd = torch.empty(d, dtype=torch.float32, device=dev)
+        if training:
+            ws = workspace(lib.b2g_bn_ws_bytes(d), dev)
+            cost(4 * m * d)
+            _run("b2g_bn_stats", lib.b2g_bn_stats, x.data_ptr(), m, d, float(eps), float(momentum), mean.data_ptr(), rstd.data_ptr(),
+                                        _ptr(running_mean), _ptr(running_var), ws.data_ptr(), ws.numel(), _stream())
+        else:
+            _run("b2g_bn_eval_stats", lib.b2g_bn_eval_stats, running_mean.data_ptr(), running_var.data_ptr(), d, float(eps), mean.data_ptr(),
+                                             rstd.data_ptr(), _stream())
+        p = float(p_drop) if training else 0.0
+        y = torch.empty_like(x)
+        cost(8 * m * d)
+        _run("b2g_bn_apply", lib.b2g_bn_apply, x.data_ptr(), m, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                    int(act), p, int(seed), int(sid), y.data_ptr(), _stream())
+        ctx.save_for_backward(x, mean, rstd, gamma, beta)
+        ctx.cfg = (int(act), p, int(seed), int(sid), bool(training))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, mean, rstd, gamma, beta = ctx.saved_tensors
+        act, p, seed, sid, training = ctx.cfg
+        dy = _f32(dy, "grad")
+        m, d = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(beta)
+        ws = workspace(lib.b2g_bn_ws_bytes(d), x.device)
+        cost(12 * m * d)
+        _run("b2g_bn_bwd", lib.b2g_bn_bwd, x.data_ptr(), dy.data_ptr(), m, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                  beta.data_ptr(), act, p, seed, sid, int(training), dx.data_ptr(), dgamma.data_ptr(),
+                                  dbeta.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
+
+
+class ActDropFn(Function):
+    """dropout(act(x)) without normalisation (use_batch_norm=False branch of model.py:259-269)."""
+
+    @staticmethod
+    def forward(ctx, x, act, p_drop, seed, sid, training):
+        lib = _lib.load()
+        x = _f32(x, "x")
+        m, d = x.shape
+        dev = x.device
+        zeros = torch.zeros(d, dtype=torch.float32, device=dev)
+        ones = torch.ones(d, dtype=torch.float32, device=dev)
+        p = float(p_drop) if training else 0.0
+        y = torch.empty_like(x)
+        _run("b2g_bn_apply", lib.b2g_bn_apply, x.data_ptr(), m, d, zeros.data_ptr(), ones.data_ptr(), ones.data_ptr(), zeros.data_ptr(),
+                                    int(act), p, int(seed), int(sid), y.data_ptr(), _stream())
+        ctx.save_for_backward(x, zeros, ones)
+        ctx.cfg = (int(act), p, int(seed), int(sid))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, zeros, ones = ctx.saved_tensors
+        act, p, seed, sid = ctx.cfg
+        dy = _f32(dy, "grad")
+        m, d = x.shape
+        dx = torch.empty_like(x)
+        ws = workspace(lib.b2g_bn_ws_bytes(d), x.device)
+        _run("b2g_bn_bwd", lib.b2g_bn_bwd, x.data_ptr(), dy.data_ptr(), m, d, zeros.data_ptr(), ones.data_ptr(), ones.data_ptr(),
+                                  zeros.data_ptr(), act, p, seed, sid, 0, dx.data_ptr(), None, None, ws.data_ptr(),
+                                  ws.numel(), _stream())
+        return dx, None, None, None, None, None
+
+
+class ReluDropoutFn(Function):
+    """dropout(relu(x)) on a flat tensor (EdgeRegressionHead: nn.ReLU -> nn.Dropout, model.py:377-380)."""
+
+    @staticmethod
+    def forward(ctx, x, relu, p_drop, seed, sid, training):
+        lib = _lib.load()
+        x = _f32(x, "x")
+        p = float(p_drop) if training else 0.0
+        y = torch.empty_like(x)
+        cost(8 * x.numel())
+        _run("b2g_relu_dropout_fwd", lib.b2g_relu_dropout_fwd, x.data_ptr(), x.numel(), int(relu), p, int(seed), int(sid), y.data_ptr(), _stream())
+        ctx.save_for_backward(y)
+        ctx.cfg = (int(relu), p, int(seed), int(sid))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        (y,) = ctx.saved_tensors
+        relu, p, seed, sid = ctx.cfg
+        dy = _f32(dy, "grad")
+        dx = torch.empty_like(y)
+        cost(12 * y.numel())
+        _run("b2g_relu_dropout_bwd", lib.b2g_relu_dropout_bwd, y.data_ptr(), dy.data_ptr(), y.numel(), relu, p, seed, sid, dx.data_ptr(), _stream())
+        return dx, None, None, None, None, None
+
+
+class L2NormFn(Function):
+    """F.normalize(x, p=2, dim=1, eps=1e-12)  (model.py:105,232)."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        lib = _lib.load()
+        x = _f32(x, "x")
+        m, d = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(m, dtype=torch.float32, device=x.device)
+        cost(8 * m * d)
+        _run("b2g_l2norm_fwd", lib.b2g_l2norm_fwd, x.data_ptr(), m, d, float(eps), y.data_ptr(), inv.data_ptr(), _stream())
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        y, inv = ctx.saved_tensors
+        dy = _f32(dy, "grad")
+        m, d = y.shape
+        dx = torch.empty_like(y)
+        cost(12 * m * d)
+        _run("b2g_l2norm_bwd", lib.b2g_l2norm_bwd, y.data_ptr(), dy.data_ptr(), inv.data_ptr(), m, d, dx.data_ptr(), _stream())
+        return dx, None
+
+
+class MeanAggFn(Function):
+    """agg[v] = mean_{u -> v} x_src[u]  with count clamped to >= 1  (PyG SAGEConv(aggr='mean').propagate,
+    called from model.py:256).  Backward walks the transposed CSR: no float atomics."""
+
+    @staticmethod
+    def forward(ctx, x_src, rel: Relation):
+        x_src = _f32(x_src, "x_src")
+        out = torch.empty((rel.n_dst, x_src.shape[1]), dtype=torch.float32, device=x_src.device)
+        gather_reduce_([rel.by_dst], [x_src], [rel.by_dst.inv_deg], [None], out, False)
+        ctx.rel = rel
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rel = ctx.rel
+        dout = _f32(dout, "grad")
+        dx = torch.empty((rel.n_src, dout.shape[1]), dtype=torch.float32, device=dout.device)
+        gather_reduce_([rel.by_src], [dout], [None], [rel.by_dst.inv_deg], dx, False)
+        return dx, None
+
+
+class SageDstFn(Function):
+    """All SAGEConv results that land on one destination node type, summed like HeteroConv(aggr='sum')
+    (PyG hetero_conv.py group(); model.py:125-131,256):
+
+        out = x_dst W_root^T + b_root                        (sum over relations of lin_r, and of lin_l's bias)
+              + sum_{small-source rels} mean_rel(Y_rel)      (Y_rel = x_src W_l^T computed on the few source rows first)
+              + sum_{big-source rels}  agg_rel W_l_rel^T     (agg_rel = mean_rel(x_src) computed first)
+
+    The re-association (A X) W = A (X W) keeps the only large-M GEMM at K = d.
+    """
+
+    @staticmethod
+    def forward(ctx, x_dst, w_root, b_root, small_rels, n_big, *tensors):
+        n_small = len(small_rels)
+        ys = [_f32(t, "Y") for t in tensors[:n_small]]
+        aggs = [_f32(t, "agg") for t in tensors[n_small:n_small + n_big]]
+        wls = [_f32(t, "W_l") for t in tensors[n_small + n_big:n_small + 2 * n_big]]
+        x_dst, w_root = _f32(x_dst, "x_dst"), _f32(w_root, "W_root")
+        b_root = None if b_root is None else _f32(b_root, "b_root")
+        out = torch.empty((x_dst.shape[0], w_root.shape[0]), dtype=torch.float32, device=x_dst.device)
+        linear_fwd_(x_dst, w_root, b_root, out)
+        for agg, wl in zip(aggs, wls):
+            linear_fwd_(agg, wl, None, out, accumulate=True)
+        if n_small:
+            gather_reduce_([r.by_dst for r in small_rels], ys, [r.by_dst.inv_deg for r in small_rels], [None] * n_small, out, True)
+        ctx.save_for_backward(x_dst, w_root, *aggs, *wls)
+        ctx.meta = (small_rels, n_big, b_root is not None, [y.shape for y in ys])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        small_rels, n_big, has_bias, y_shapes = ctx.meta
+        saved = ctx.saved_tensors
+        x_dst, w_root = saved[0], saved[1]
+        aggs, wls = saved[2:2 + n_big], saved[2 + n_big:2 + 2 * n_big]
+        dout = _f32(dout, "grad")
+        n_small = len(small_rels)
+        nig = ctx.needs_input_grad
+        dx = dw = db = None
+        if nig[0]:
+            dx = torch.empty_like(x_dst)
+            linear_bwd_input_(dout, w_root, dx)
+        need_b = has_bias and nig[2]
+        if nig[1] or need_b:
+            dw = torch.empty_like(w_root)
+            db = torch.empty(w_root.shape[0], dtype=torch.float32, device=dout.device) if need_b else None
+            linear_bwd_weight_(dout, x_dst, dw, db)
+        d_ys: List[Optional[torch.Tensor]] = []
+        for k, rel in enumerate(small_rels):
+            if nig[5 + k]:
+                dy = torch.empty(y_shapes[k], dtype=torch.float32, device=dout.device)
+                gather_reduce_([rel.by_src], [dout], [None], [rel.by_dst.inv_deg], dy, False)
+                d_ys.append(dy)
+            else:
+                d_ys.append(None)
+        d_aggs, d_wls = [], []
+        for k in range(n_big):
+            if nig[5 + n_small + k]:
+                da = torch.empty_like(aggs[k])
+                linear_bwd_input_(dout, wls[k], da)
+                d_aggs.append(da)
+            else:
+                d_aggs.append(None)
+            if nig[5 + n_small + n_big + k]:
+                dwl = torch.empty_like(wls[k])
+                linear_bwd_weight_(dout, aggs[k], dwl, None)
+                d_wls.append(dwl)
+            else:
+                d_wls.append(None)
+        return (dx, dw, db, None, None, *d_ys, *d_aggs, *d_wls)
+
+
+class PairAddReluFn(Function):
+    """z[i] = relu(U[p_i] + V[l_i]) -- the first decoder layer after factorising
+    Linear(2d, 64)(cat[h_p, h_l]) = h_p W[:, :d]^T + (h_l W[:, d:]^T + b)   (model.py:305-309,324-333,373-377):
+    the per-pair [M, 2d] concatenation and its index_put backward are never materialised."""
+
+    @staticmethod
+    def forward(ctx, u, v, pairs: PairIndex):
+        lib = _lib.load()
+        u, v = _f32(u, "U"), _f32(v, "V")
+        d = u.shape[1]
+        z = torch.empty((pairs.m, d), dtype=torch.float32, device=u.device)
+        cost(4 * pairs.m * d + 16 * pairs.m + 4 * (u.numel() + v.numel()))
+        _run("b2g_gather_add_rows", lib.b2g_gather_add_rows, u.data_ptr(), pairs.patient_idx.data_ptr(), v.data_ptr(), pairs.lab_idx.data_ptr(),
+                                           pairs.m, d, 1, z.data_ptr(), _stream())
+        ctx.save_for_backward(z)
+        ctx.meta = (pairs, u.shape, v.shape)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _lib.load()
+        (z,) = ctx.saved_tensors
+        pairs, u_shape, v_shape = ctx.meta
+        dz = _f32(dz, "grad")
+        g = torch.empty_like(z)
+        cost(12 * z.numel())
+        _run("b2g_relu_dropout_bwd", lib.b2g_relu_dropout_bwd, z.data_ptr(), dz.data_ptr(), z.numel(), 1, 0.0, 0, 0, g.data_ptr(), _stream())
+        du = dv = None
+        if ctx.needs_input_grad[0]:
+            du = torch.empty(u_shape, dtype=torch.float32, device=dz.device)
+            gather_reduce_([pairs.by_patient], [g], [None], [None], du, False)
+        if ctx.needs_input_grad[1]:
+            dv = torch.empty(v_shape, dtype=torch.float32, device=dz.device)
+            gather_reduce_([pairs.by_lab], [g], [None], [None], dv, False)
+        return du, dv, None
+
+
+class GatherRowsFn(Function):
+    """table[idx]  (nn.Embedding lookup, model.py:225-226, for index sets other than arange)."""
+
+    @staticmethod
+    def forward(ctx, table, idx):
+        lib = _lib.load()
+        table = _f32(table, "table")
+        idx = idx.contiguous()
+        if idx.dtype != torch.int64:
+            idx = idx.long()
+        out = torch.empty((idx.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
+        _run("b2g_gather_rows", lib.b2g_gather_rows, table.data_ptr(), idx.data_ptr(), idx.numel(), table.shape[0], table.shape[1],
+                                       out.data_ptr(), _stream())
+        ctx.idx = idx
+        ctx.n = table.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _f32(dout, "grad")
+        csr = CSR(ctx.idx, ctx.idx, ctx.n, ctx.n, col_is_eid=True)
+        dt = torch.empty((ctx.n, dout.shape[1]), dtype=torch.float32, device=dout.device)
+        gather_reduce_([csr], [dout], [None], [None], dt, False)
+        return dt, None
+
+
+class WeightedLossFn(Function):
+    """mean over supervised pairs of w[lab] * (|p - t| | (p - t)^2 | huber)  (train.py:364-386,
+    model.py:602-605).  One fused reduction; the gradient is produced in the same call."""
+
+    @staticmethod
+    def forward(ctx, pred, target, lab, w, sup, kind):
+        lib = _lib.load()
+        pred, target = _f32(pred, "pred"), _f32(target, "target")
+        m = pred.numel()
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        grad = torch.empty_like(pred)
+        if sup is not None:
+            sup = sup.contiguous()
+            sup = sup.view(torch.uint8) if sup.dtype == torch.bool else sup.to(torch.uint8)
+        ws = workspace(lib.b2g_loss_ws_bytes(m), pred.device)
+        _run("b2g_weighted_loss", lib.b2g_weighted_loss, pred.data_ptr(), target.data_ptr(), _ptr(lab), _ptr(w), _ptr(sup), m, int(kind),
+                                         loss.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return grad * dloss, None, None, None, None, None
+
+
+LOSS_KINDS = {"mae": 0, "mse": 1, "huber": 2}
+
+
+def weighted_loss(pred, target, lab_idx=None, lab_weights=None, sup_mask=None, loss_type="mae"):
+    if loss_type not in LOSS_KINDS:
+        raise ValueError(f"Unknown loss type: {loss_type}")
+    return WeightedLossFn.apply(pred, target, lab_idx, lab_weights, sup_mask, LOSS_KINDS[loss_type])

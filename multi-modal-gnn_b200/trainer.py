@@ -1,0 +1,172 @@
+"""Host side of the training step: the hot part of the reference's ``src/train.py`` (EdgeMasker,
+Trainer._compute_lab_weights / train_epoch / validate) with the same names, argument meaning and error
+behaviour, driving the CUDA model.  The reference's own ``train.py`` can also drive the model unchanged
+(INTEGRATION.md); this module exists because the reference is absent on the GPU box and because its
+loss/selection tail is fused here into one kernel (``ops.weighted_loss``).
+
+Integer / boolean work (splits, supervision masks) stays on the host with torch's CPU generator so it
+is bit-exact with the reference.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+from .model import compute_regression_loss
+
+
+class EdgeMasker:
+    """train.py:37-176.  70/15/15 edge split by seeded CPU randperm; per-epoch 20 % supervision mask."""
+
+    def __init__(self, data, train_split: float = 0.7, val_split: float = 0.15, test_split: float = 0.15,
+                 mask_fraction: float = 0.2, seed: int = 42):
+        assert abs(train_split + val_split + test_split - 1.0) < 1e-6, "Splits must sum to 1.0"
+        self.data = data
+        self.train_split, self.val_split, self.test_split = train_split, val_split, test_split
+        self.mask_fraction, self.seed = mask_fraction, seed
+        self.edge_type = ("patient", "has_lab", "lab")
+        self.edge_index = data[self.edge_type].edge_index
+        self.edge_attr = data[self.edge_type].edge_attr
+        self.num_edges = int(self.edge_index.shape[1])
+        self.train_mask, self.val_mask, self.test_mask = self._create_splits()
+        self._split_cache: Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+
+    def _create_splits(self):
+        """train.py:98-129 (host, CPU generator: bit-exact with the reference for the same seed)."""
+        torch.manual_seed(self.seed)
+        perm = torch.randperm(self.num_edges)
+        n_train = int(self.train_split * self.num_edges)
+        n_val = int(self.val_split * self.num_edges)
+        masks = [torch.zeros(self.num_edges, dtype=torch.bool) for _ in range(3)]
+        masks[0][perm[:n_train]] = True
+        masks[1][perm[n_train:n_train + n_val]] = True
+        masks[2][perm[n_train + n_val:]] = True
+        return masks
+
+    def split_mask(self, split: str) -> torch.Tensor:
+        if split == "train":
+            return self.train_mask
+        if split == "val":
+            return self.val_mask
+        if split == "test":
+            return self.test_mask
+        raise ValueError(f"Unknown split: {split}")
+
+    def supervision_mask(self, split: str, seed: Optional[int] = None) -> torch.Tensor:
+        """train.py:150-165 (host).  ``seed=None`` reproduces the reference's wall-clock reseeding."""
+        n = int(self.split_mask(split).sum())
+        if split == "train" and self.mask_fraction > 0:
+            torch.manual_seed(int(time.time()) if seed is None else int(seed))
+            return torch.rand(n) < self.mask_fraction
+        return torch.ones(n, dtype=torch.bool)
+
+    def split_edges(self, split: str):
+        """(edge_indices [2, n], edge_values [n]) of a split, on the graph's device (cached: static)."""
+        if split not in self._split_cache:
+            mask = self.split_mask(split).to(self.edge_index.device)
+            ei = self.edge_index[:, mask].contiguous()
+            self._split_cache[split] = (ei, self.edge_attr[mask].squeeze(-1).contiguous(), ei[0], ei[1])
+        return self._split_cache[split][:2]
+
+    def split_rows(self, split: str):
+        """(patient_indices, lab_indices) views of split_edges(split)[0]; the same tensor objects every call."""
+        self.split_edges(split)
+        return self._split_cache[split][2:]
+
+    def get_masked_data(self, split: str = "train", seed: Optional[int] = None):
+        """train.py:131-176: (edge_indices, edge_values, mask, supervision_mask)."""
+        mask = self.split_mask(split)
+        sup = self.supervision_mask(split, seed)
+        ei, ev = self.split_edges(split)
+        return ei, ev, mask, sup
+
+
+def compute_lab_weights(lab_indices: torch.Tensor, edge_values: torch.Tensor, num_labs: int) -> torch.Tensor:
+    """Trainer._compute_lab_weights (train.py:295-330): 1 / (unbiased variance + 1e-6) per lab over the
+    train split (variance := 1 for labs with < 2 samples), rescaled to sum to num_labs.  One-off, O(E)."""
+    v = edge_values.double()
+    cnt = torch.zeros(num_labs, dtype=torch.float64, device=v.device).index_add_(0, lab_indices, torch.ones_like(v))
+    s1 = torch.zeros(num_labs, dtype=torch.float64, device=v.device).index_add_(0, lab_indices, v)
+    mean = s1 / cnt.clamp(min=1)
+    s2 = torch.zeros(num_labs, dtype=torch.float64, device=v.device).index_add_(0, lab_indices, (v - mean[lab_indices]) ** 2)
+    var = torch.where(cnt > 1, s2 / (cnt - 1).clamp(min=1), torch.ones_like(s2))
+    w = 1.0 / (var.float() + 1e-6)
+    return w * num_labs / w.sum()
+
+
+class Trainer:
+    """train.py:183-431 (optimizer/scheduler construction, lab weights, train_epoch, validate)."""
+
+    def __init__(self, model, data, masker: EdgeMasker, config: Dict, device: torch.device):
+        self.model = model.to(device)
+        self.data = data.to(device)
+        self.masker = masker
+        masker.edge_index = self.data[masker.edge_type].edge_index
+        masker.edge_attr = self.data[masker.edge_type].edge_attr
+        masker._split_cache.clear()
+        self.config, self.device = config, device
+        tc = config["train"]
+        self.optimizer = self._build_optimizer(tc["optimizer"])
+        self.scheduler = self._build_scheduler(tc.get("lr_scheduler", {}))
+        self.loss_fn = tc["loss"]
+        self.epochs = tc["epochs"]
+        self.early_stopping_patience = tc["early_stopping_patience"]
+        self.best_val_loss, self.patience_counter = float("inf"), 0
+        self.train_losses, self.val_losses = [], []
+        self.lab_weights = self._compute_lab_weights()
+
+    def _build_optimizer(self, oc):
+        kind = oc.get("type", "adam").lower()
+        if kind == "adam":
+            return torch.optim.Adam(self.model.parameters(), lr=oc["lr"], weight_decay=oc["weight_decay"])
+        if kind == "sgd":
+            return torch.optim.SGD(self.model.parameters(), lr=oc["lr"], weight_decay=oc["weight_decay"],
+                                   momentum=oc.get("momentum", 0.9))
+        raise ValueError(f"Unknown optimizer: {kind}")
+
+    def _build_scheduler(self, sc):
+        if not sc.get("enabled", False):
+            return None
+        kind = sc.get("type", "reduce_on_plateau")
+        if kind == "reduce_on_plateau":
+            return torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode="min", factor=sc.get("factor", 0.5),
+                                                              patience=sc.get("patience", 10))
+        if kind == "step":
+            return torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=sc.get("step_size", 30), gamma=sc.get("gamma", 0.1))
+        raise ValueError(f"Unknown scheduler: {kind}")
+
+    def _compute_lab_weights(self) -> torch.Tensor:
+        ei, ev = self.masker.split_edges("train")
+        return compute_lab_weights(ei[1], ev, int(self.data["lab"].num_nodes))
+
+    def train_step(self, patient_indices, lab_indices, edge_values, supervision_mask) -> torch.Tensor:
+        """Body of train_epoch (train.py:356-390) on device tensors; returns the loss tensor (no host sync)."""
+        self.optimizer.zero_grad()
+        pred = self.model.predict_lab_values(self.data, patient_indices, lab_indices)
+        if self.loss_fn in ("mae", "mse"):
+            loss = ops.weighted_loss(pred, edge_values, lab_indices, self.lab_weights, supervision_mask, self.loss_fn)
+        else:   # train.py:378-383: unweighted fallback over the supervised subset
+            loss = ops.weighted_loss(pred, edge_values, None, None, supervision_mask, self.loss_fn)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def train_epoch(self, seed: Optional[int] = None) -> float:
+        """train.py:332-392."""
+        self.model.train()
+        _, ev, _, sup = self.masker.get_masked_data("train", seed)
+        pi, li = self.masker.split_rows("train")
+        sup_dev = sup.to(self.device, non_blocking=True)
+        return float(self.train_step(pi, li, ev, sup_dev).item())
+
+    @torch.no_grad()
+    def validate(self, split: str = "val") -> float:
+        """train.py:394-431."""
+        self.model.eval()
+        _, ev, _, _ = self.masker.get_masked_data(split)
+        pi, li = self.masker.split_rows(split)
+        pred = self.model.predict_lab_values(self.data, pi, li)
+        return float(compute_regression_loss(pred, ev, loss_type=self.loss_fn).item())

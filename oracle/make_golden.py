@@ -57,17 +57,23 @@ def run_case(spec_name, loss, store_state, store_all_grads):
     torch.manual_seed(sup_seed)
     ei_train = masker.edge_index[:, masker.train_mask]
     sup_mask = torch.rand(int(masker.train_mask.sum())) < 0.2
-    # eval-mode products with the post-step state
-    model.eval()
-    with torch.no_grad():
-        ei_val = masker.edge_index[:, masker.val_mask]
-        pred_val = model.predict_lab_values(d, ei_val[0], ei_val[1])
-        enc = model.encode_nodes(d)
-        fwd = model(d)
-        ei_all = masker.edge_index
-        pred_all = model.predict_lab_values(d, ei_all[0], ei_all[1])
+    # eval-mode products at a fully stored state: the *before* parameters + the BN buffers after the step
     loss_val = trainer.validate("val")
     loss_test = trainer.validate("test")
+    eval_state = dict(before)
+    eval_state.update({k: v for k, v in after.items() if "running" in k or "num_batches" in k})
+    model3 = M.build_model(cfg, (d.node_types, d.edge_types), None)
+    model3._init_embeddings(d)
+    model3.load_state_dict(eval_state)
+    model3.eval()
+    with torch.no_grad():
+        ei_val = masker.edge_index[:, masker.val_mask]
+        pred_val = model3.predict_lab_values(d, ei_val[0], ei_val[1])
+        enc = model3.encode_nodes(d)
+        fwd = model3(d)
+        ei_all = masker.edge_index
+        pred_all = model3.predict_lab_values(d, ei_all[0], ei_all[1])
+        eval_loss_val = float(M.compute_regression_loss(pred_val, masker.edge_attr[masker.val_mask].squeeze(-1), loss))
     # train-mode prediction replay from the *before* state (fresh model so BN buffers start equal)
     model2 = M.build_model(cfg, (d.node_types, d.edge_types), None)
     model2._init_embeddings(d)
@@ -82,7 +88,7 @@ def run_case(spec_name, loss, store_state, store_all_grads):
         "split": {"train": masker.train_mask, "val": masker.val_mask, "test": masker.test_mask},
         "sup_seed": sup_seed, "sup_mask": sup_mask, "lab_weights": trainer.lab_weights.clone(),
         "loss_train": float(loss_train), "loss_val": float(loss_val), "loss_test": float(loss_test),
-        "pred_train": pred_train, "pred_val": pred_val, "pred_all": pred_all,
+        "pred_train": pred_train, "pred_val": pred_val, "pred_all": pred_all, "eval_loss_val": eval_loss_val,
         "degree": torch.bincount(masker.edge_index[0], minlength=int(g["patient"].num_nodes)),
         "state_keys": list(before.keys()),
         "state_checksum": {k: float(v.double().sum()) for k, v in before.items()},
@@ -91,16 +97,13 @@ def run_case(spec_name, loss, store_state, store_all_grads):
         "grad_norm": {n: float(v.double().norm()) for n, v in grads.items() if v is not None},
         "optimizer_param_count": sum(p.numel() for grp in trainer.optimizer.param_groups for p in grp["params"]),
     }
+    blob["state_before"] = before
     if store_state:
-        blob["state_before"] = before
         blob["encode_eval"] = enc
         blob["forward_eval"] = fwd
         blob["after_params"] = {k: after[k] for k in ("patient_transform.0.weight", "edge_predictor.mlp.0.weight",
                                                       "convs.0.convs.lab__has_lab_rev__patient.lin_l.weight",
                                                       "batch_norms.0.patient.weight")}
-    else:
-        blob["state_seed"] = None
-        blob["state_before"] = before
     if store_all_grads:
         blob["grads"] = {n: v for n, v in grads.items() if v is not None}
     else:

@@ -1,0 +1,452 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every check goes through libb2g's C ABI
+(ctypes) and is compared with the CPU oracle (oracle/hetero_rgcn_ref.py) or with the golden vectors the
+unmodified reference produced (tests/golden/).
+
+Tolerances (BASELINE.json north_star): bit-exact for CSR / degrees / masks; <= 1e-5 relative for fp32
+aggregation; fp32 dense layers <= 1e-4 relative (different summation order only)."""
+import importlib
+
+import pytest
+import torch
+
+from conftest import golden_graph
+from oracle import hetero_rgcn_ref as R
+
+pytestmark = pytest.mark.gpu
+
+PKG = "multi-modal-gnn_b200"
+
+
+def _mods():
+    return (importlib.import_module(PKG), importlib.import_module(PKG + ".graph"), importlib.import_module(PKG + ".ops"),
+            importlib.import_module(PKG + ".model"), importlib.import_module(PKG + ".trainer"), importlib.import_module(PKG + "._lib"))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def relerr(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------------------------------------------
+# (a) CSR / degrees / gate: bit-exact
+# ------------------------------------------------------------------------------------------------------
+def _check_csr(G, key, val, n_rows, n_vals, dev):
+    csr = G.CSR(key.to(dev), val.to(dev), n_rows, n_vals)
+    order = torch.argsort(key, stable=True)
+    deg = torch.bincount(key, minlength=n_rows)
+    rowptr = torch.zeros(n_rows + 1, dtype=torch.int64)
+    rowptr[1:] = deg.cumsum(0)
+    assert torch.equal(csr.rowptr.cpu().long(), rowptr)
+    e = key.numel()
+    if e:
+        assert torch.equal(csr.eid.cpu().long()[:e], order)
+        assert torch.equal(csr.col.cpu().long()[:e], val[order])
+    assert csr.deg.dtype == torch.int64 and torch.equal(csr.deg.cpu(), deg)
+    torch.testing.assert_close(csr.inv_deg.cpu(), 1.0 / deg.clamp(min=1).float(), rtol=0, atol=0)
+    return csr
+
+
+@pytest.mark.parametrize("e,n_rows,n_vals", [(0, 7, 5), (1, 1, 1), (33, 5, 9), (4097, 50, 300), (100_000, 1834, 50),
+                                             (300_000, 70_000, 200), (2_000_000, 300_000, 160), (50_000, 1 << 20, 3)])
+def test_csr_build_bit_exact(e, n_rows, n_vals, dev):
+    _, G, *_ = _mods()
+    g = torch.Generator().manual_seed(e + n_rows)
+    key = torch.randint(0, n_rows, (e,), generator=g)
+    val = torch.randint(0, n_vals, (e,), generator=g)
+    if e > 100:  # leave some rows empty and one row heavy
+        key[key % 7 == 3] = 0
+    _check_csr(G, key, val, n_rows, n_vals, dev)
+
+
+def test_csr_rejects_out_of_range(dev):
+    pkg, G, *_ = _mods()
+    key = torch.tensor([0, 1, 5], device=dev)
+    val = torch.tensor([0, 0, 0], device=dev)
+    with pytest.raises(RuntimeError):
+        G.CSR(key, val, 5, 1)
+    g = pkg.synth.make_graph("tiny").to(dev)
+    g["patient", "has_lab", "lab"].edge_index[1, 0] = 10_000
+    with pytest.raises(ValueError):
+        G.GraphIndex(g)
+
+
+def test_graph_index_degrees_and_gate(dev):
+    pkg, G, ops, M, T, L = _mods()
+    g = pkg.synth.make_graph("C1")
+    gi = G.GraphIndex(pkg.synth.make_graph("C1").to(dev))
+    ei = g["patient", "has_lab", "lab"].edge_index
+    deg = torch.bincount(ei[0], minlength=1834)
+    assert torch.equal(gi.patient_lab_degree.cpu(), deg)
+    # forward CSR of has_lab_rev == transposed CSR of has_lab (same edge set, SURVEY.md section 3.5 iii)
+    a, b = gi.relations[("lab", "has_lab_rev", "patient")].by_dst, gi.relations[("patient", "has_lab", "lab")].by_src
+    assert torch.equal(a.rowptr, b.rowptr) and torch.equal(a.col, b.col)
+    pi = ei[0][::7].contiguous()
+    low = torch.empty(pi.numel(), dtype=torch.uint8, device=dev)
+    L.check(L.load().b2g_degree_gate(gi.patient_lab_degree.data_ptr(), pi.to(dev).data_ptr(), pi.numel(), 6, low.data_ptr(), None))
+    assert torch.equal(low.cpu().bool(), deg[pi] < 6)
+    for et, rel in gi.relations.items():
+        e = g[et].edge_index.shape[1]
+        assert int(rel.by_dst.rowptr[-1]) == e and int(rel.by_src.rowptr[-1]) == e
+        assert int(rel.by_dst.deg.sum()) == e
+
+
+# ------------------------------------------------------------------------------------------------------
+# (b) message passing
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("spec,d", [("tiny", 128), ("C1", 128), ("C1", 64), ("tiny", 256), ("tiny", 32)])
+def test_mean_aggregate_fwd_bwd(spec, d, dev):
+    pkg, G, ops, *_ = _mods()
+    g = pkg.synth.make_graph(spec)
+    gi = G.GraphIndex(pkg.synth.make_graph(spec).to(dev))
+    gen = torch.Generator().manual_seed(0)
+    for et in g.edge_types:
+        rel = gi.relations[et]
+        x = torch.randn(rel.n_src, d, generator=gen)
+        go = torch.randn(rel.n_dst, d, generator=gen)
+        xr = x.clone().double().requires_grad_(True)
+        ref = R.mean_aggregate(xr, g[et].edge_index, rel.n_dst)
+        ref.backward(go.double())
+        xd = x.to(dev).requires_grad_(True)
+        out = ops.MeanAggFn.apply(xd, rel)
+        out.backward(go.to(dev))
+        assert relerr(out, ref.detach()) <= 1e-5, et
+        assert relerr(xd.grad, xr.grad) <= 1e-5, et
+        out2 = ops.MeanAggFn.apply(xd, rel)
+        assert torch.equal(out, out2), "aggregation must be run-to-run bit-identical"
+
+
+def test_aggregate_isolated_destinations_are_zero(dev):
+    pkg, G, ops, *_ = _mods()
+    g = pkg.synth.make_graph("C1").to(dev)
+    gi = G.GraphIndex(g)
+    rel = gi.relations[("diagnosis", "has_diagnosis_rev", "patient")]
+    iso = (rel.by_dst.deg == 0)
+    assert int(iso.sum()) > 0
+    out = ops.MeanAggFn.apply(torch.randn(rel.n_src, 128, device=dev), rel)
+    assert float(out[iso].abs().max()) == 0.0
+
+
+def test_aggregate_linearity_and_ones_at_bench_size(dev):
+    """Size-independent properties at the benchmark configuration (C2)."""
+    pkg, G, ops, *_ = _mods()
+    g = pkg.synth.make_graph("C2").to(dev)
+    gi = G.GraphIndex(g)
+    for et in [("lab", "has_lab_rev", "patient"), ("patient", "has_lab", "lab"), ("patient", "has_medication", "medication")]:
+        rel = gi.relations[et]
+        for csr in (rel.by_dst, rel.by_src):
+            e = csr.n_edges
+            assert int(csr.rowptr[-1]) == e
+            assert bool((csr.rowptr[1:] >= csr.rowptr[:-1]).all())
+            assert torch.equal(torch.sort(csr.eid[:e].long())[0], torch.arange(e, device=dev))
+            interior = torch.ones(e, dtype=torch.bool, device=dev)
+            interior[csr.rowptr[:-1][csr.deg > 0].long()] = False
+            assert bool((csr.eid[1:e][interior[1:]] > csr.eid[: e - 1][interior[1:]]).all()), "rows must keep edge order"
+        ones = torch.ones(rel.n_src, 128, device=dev)
+        m = ops.MeanAggFn.apply(ones, rel)
+        has = rel.by_dst.deg > 0
+        assert float((m[has] - 1).abs().max()) <= 1e-5 and float(m[~has].abs().sum()) == 0.0
+        a, b = torch.randn(rel.n_src, 128, device=dev), torch.randn(rel.n_src, 128, device=dev)
+        lhs = ops.MeanAggFn.apply(2.0 * a - 3.0 * b, rel)
+        rhs = 2.0 * ops.MeanAggFn.apply(a, rel) - 3.0 * ops.MeanAggFn.apply(b, rel)
+        assert float((lhs - rhs).abs().max()) <= 2e-5 * float(rhs.abs().max().clamp_min(1))
+
+
+# ------------------------------------------------------------------------------------------------------
+# (d) dense, BN, L2 norm, dropout, loss
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,k,n,bias", [(1, 128, 128, True), (300, 128, 128, True), (1834, 128, 64, False), (5000, 64, 32, True),
+                                        (5000, 32, 1, True), (777, 256, 64, True), (129, 128, 128, False), (4099, 256, 256, True)])
+def test_linear_fwd_bwd(m, k, n, bias, dev):
+    *_, ops, M, T, L = _mods()
+    gen = torch.Generator().manual_seed(m + n)
+    x, w = torch.randn(m, k, generator=gen), torch.randn(n, k, generator=gen) / k ** 0.5
+    b = torch.randn(n, generator=gen) if bias else None
+    go = torch.randn(m, n, generator=gen)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    br = b.double().requires_grad_(True) if bias else None
+    yr = torch.nn.functional.linear(xr, wr, br)
+    yr.backward(go.double())
+    xd, wd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+    bd = b.to(dev).requires_grad_(True) if bias else None
+    y = ops.linear(xd, wd, bd)
+    y.backward(go.to(dev))
+    assert relerr(y, yr.detach()) <= 1e-5
+    assert relerr(xd.grad, xr.grad) <= 1e-5
+    assert relerr(wd.grad, wr.grad) <= 2e-5
+    if bias:
+        assert relerr(bd.grad, br.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("m,d,act,p", [(50, 128, 1, 0.0), (1834, 128, 1, 0.0), (20000, 64, 1, 0.0), (300, 256, 0, 0.0),
+                                       (1834, 128, 2, 0.0), (1834, 128, 3, 0.0), (1834, 128, 1, 0.2)])
+def test_batchnorm_act_dropout(m, d, act, p, dev):
+    *_, ops, M, T, L = _mods()
+    gen = torch.Generator().manual_seed(m)
+    x = torch.randn(m, d, generator=gen) * 2 + 0.5
+    gamma, beta = 1 + 0.1 * torch.randn(d, generator=gen), 0.1 * torch.randn(d, generator=gen)
+    go = torch.randn(m, d, generator=gen)
+    seed, sid = 12345, 3
+    mask = ops.dropout_mask(m * d, p, seed, sid, dev).cpu().view(m, d).double() if p > 0 else None
+    if p > 0:
+        keep = float((mask > 0).double().mean())
+        assert abs(keep - (1 - p)) < 0.01 and abs(float(mask.max()) - 1 / (1 - p)) < 1e-6
+    acts = {0: lambda t: t, 1: torch.relu, 2: lambda t: torch.nn.functional.leaky_relu(t, 0.01), 3: torch.nn.functional.elu}
+    for training in (True, False):
+        rm, rv = torch.zeros(d) + 0.1, torch.ones(d) * 1.5
+        rm_d, rv_d = rm.clone().to(dev), rv.clone().to(dev)
+        xr, gr, br = x.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+        rm_r, rv_r = rm.double(), rv.double()
+        yr = acts[act](torch.nn.functional.batch_norm(xr, rm_r, rv_r, gr, br, training, 0.1, 1e-5))
+        if training and p > 0:
+            yr = yr * mask
+        yr.backward(go.double())
+        xd, gd, bd = x.to(dev).requires_grad_(True), gamma.to(dev).requires_grad_(True), beta.to(dev).requires_grad_(True)
+        y = ops.BNActDropFn.apply(xd, gd, bd, rm_d, rv_d, training, act, p, seed, sid, 1e-5, 0.1)
+        y.backward(go.to(dev))
+        assert relerr(y, yr.detach()) <= 2e-5
+        assert relerr(xd.grad, xr.grad) <= 1e-4
+        assert relerr(gd.grad, gr.grad) <= 1e-4 and relerr(bd.grad, br.grad) <= 1e-4
+        assert relerr(rm_d, rm_r) <= 1e-6 and relerr(rv_d, rv_r) <= 1e-6
+
+
+@pytest.mark.parametrize("m,d", [(1, 128), (1834, 128), (999, 64), (100, 256)])
+def test_l2norm(m, d, dev):
+    *_, ops, M, T, L = _mods()
+    gen = torch.Generator().manual_seed(d)
+    x = torch.randn(m, d, generator=gen)
+    x[0] = 0.0                      # clamp branch: x / max(0, eps) = 0
+    go = torch.randn(m, d, generator=gen)
+    xr = x.double().requires_grad_(True)
+    yr = torch.nn.functional.normalize(xr, p=2.0, dim=1, eps=1e-12)
+    yr.backward(go.double())
+    xd = x.to(dev).requires_grad_(True)
+    y = ops.L2NormFn.apply(xd, 1e-12)
+    y.backward(go.to(dev))
+    assert relerr(y, yr.detach()) <= 1e-6
+    assert relerr(xd.grad[1:], xr.grad[1:]) <= 1e-5
+
+
+@pytest.mark.parametrize("kind", ["mae", "mse", "huber"])
+def test_weighted_loss(kind, dev):
+    *_, ops, M, T, L = _mods()
+    gen = torch.Generator().manual_seed(1)
+    m, nl = 43038, 50
+    p, t = torch.randn(m, generator=gen), torch.randn(m, generator=gen)
+    lab = torch.randint(0, nl, (m,), generator=gen)
+    w = torch.rand(nl, generator=gen) + 0.5
+    sup = torch.rand(m, generator=gen) < 0.2
+    pr = p.double().requires_grad_(True)
+    ref = R.weighted_loss(pr, t.double(), lab, w.double(), sup, kind)
+    ref.backward()
+    pd = p.to(dev).requires_grad_(True)
+    if kind == "huber":
+        loss = ops.weighted_loss(pd, t.to(dev), None, None, sup.to(dev), kind)
+    else:
+        loss = ops.weighted_loss(pd, t.to(dev), lab.to(dev), w.to(dev), sup.to(dev), kind)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-6 * abs(float(ref))
+    assert relerr(pd.grad, pr.grad) <= 1e-6
+    # unweighted, all pairs == compute_regression_loss (model.py:579-612)
+    l2 = M.compute_regression_loss(p.to(dev), t.to(dev), kind)
+    assert abs(float(l2) - float(R.regression_loss(p.double(), t.double(), kind))) <= 1e-6
+    with pytest.raises(ValueError):
+        M.compute_regression_loss(p.to(dev), t.to(dev), "nope")
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole path against golden vectors of the unmodified reference
+# ------------------------------------------------------------------------------------------------------
+def _model_from_golden(blob, dev, dropout=0.0, state=None):
+    pkg, G, ops, M, T, L = _mods()
+    counts, ets, eid, attr = golden_graph(blob)
+    g = pkg.HeteroGraph()
+    for nt, n in counts.items():
+        g[nt].num_nodes = n
+    for et in ets:
+        g[et].edge_index = eid[et].to(dev)
+    g["patient", "has_lab", "lab"].edge_attr = attr.to(dev)
+    cfg = {"model": {"architecture": "RGCN", "hidden_dim": 128, "num_layers": 2, "dropout": dropout, "use_batch_norm": True,
+                     "activation": "relu"}}
+    model = M.build_model(cfg, (list(counts), ets), None).to(dev)
+    model._init_embeddings(g)
+    model.load_state_dict(state if state is not None else blob["state_before"])
+    return model, g, counts, ets, eid, attr
+
+
+@pytest.mark.parametrize("fixture", ["golden_tiny_mae", "golden_tiny_mse", "golden_c1"])
+def test_train_step_matches_reference_golden(fixture, request, dev):
+    pkg, G, ops, M, T, L = _mods()
+    blob = request.getfixturevalue(fixture)
+    model, g, counts, ets, eid, attr = _model_from_golden(blob, dev)
+    assert sum(p.numel() for n, p in model.named_parameters() if not n.startswith("embeddings.")) == 483970   # KA-1
+    ei = eid[("patient", "has_lab", "lab")]
+    tr = blob["split"]["train"]
+    pi, li, tgt = ei[0][tr].to(dev), ei[1][tr].to(dev), attr[tr].squeeze(-1).to(dev)
+    w = T.compute_lab_weights(li, tgt, counts["lab"])
+    torch.testing.assert_close(w.cpu(), blob["lab_weights"], rtol=1e-5, atol=1e-7)
+    model.train()
+    pred = model.predict_lab_values(g, pi, li)
+    loss = ops.weighted_loss(pred, tgt, li, w, blob["sup_mask"].to(dev), blob["loss_fn"])
+    loss.backward()
+    assert relerr(pred, blob["pred_train"]) <= 5e-5
+    assert abs(float(loss) - blob["loss_train"]) <= 2e-5 * abs(blob["loss_train"])
+    params = dict(model.named_parameters())
+    none_keys = sorted(k for k, p in params.items() if p.grad is None)
+    assert none_keys == blob["grad_is_none"]                                  # N8 dead branches
+    for k, gref in blob["grads"].items():
+        if k in ("patient_transform.0.bias", "patient_transform.4.bias") or k.endswith("lin_l.bias"):
+            assert float(params[k].grad.abs().max()) < 1e-6, k                # exact zero up to rounding
+            continue
+        assert relerr(params[k].grad, gref) <= 2e-4, k
+    for k, gn in blob["grad_norm"].items():
+        if k in ("patient_transform.0.bias", "patient_transform.4.bias") or k.endswith("lin_l.bias"):
+            continue
+        assert abs(float(params[k].grad.double().norm()) - gn) <= 2e-4 * gn, k
+    sd = model.state_dict()
+    for k, v in blob["after_buffers"].items():                                # N3: patient MLP BNs updated twice
+        if v.dtype == torch.long:
+            assert int(sd[k]) == int(v), k
+        else:
+            assert relerr(sd[k], v) <= 1e-5, k
+
+
+def test_eval_products_match_reference_golden(golden_tiny_mae, dev):
+    pkg, G, ops, M, T, L = _mods()
+    blob = golden_tiny_mae
+    state = dict(blob["state_before"])
+    state.update(blob["after_buffers"])
+    model, g, counts, ets, eid, attr = _model_from_golden(blob, dev, dropout=0.2, state=state)
+    model.eval()
+    ei = eid[("patient", "has_lab", "lab")]
+    with torch.no_grad():
+        enc = model.encode_nodes(g)
+        fwd = model(g)
+        va = blob["split"]["val"]
+        pred_val = model.predict_lab_values(g, ei[0][va].to(dev), ei[1][va].to(dev))
+        pred_all = model.predict_lab_values(g, ei[0].to(dev), ei[1].to(dev))
+        lv = M.compute_regression_loss(pred_val, attr[va].squeeze(-1).to(dev), "mae")
+    for nt in counts:
+        assert relerr(enc[nt], blob["encode_eval"][nt]) <= 2e-5, nt
+        assert relerr(fwd[nt], blob["forward_eval"][nt]) <= 5e-5, nt
+    assert relerr(pred_val, blob["pred_val"]) <= 5e-5
+    assert relerr(pred_all, blob["pred_all"]) <= 5e-5
+    assert abs(float(lv) - blob["eval_loss_val"]) <= 2e-5 * abs(blob["eval_loss_val"])
+    # the gate really split this call across both heads
+    low = blob["degree"][ei[0]] < 6
+    assert 0 < int(low.sum()) < low.numel()
+
+
+def test_dropout_training_step_with_replayed_masks(dev):
+    """dropout > 0: device Philox masks are replayed into the CPU oracle (quirk N3: two encodes)."""
+    pkg, G, ops, M, T, L = _mods()
+    g = pkg.synth.make_graph("tiny", seed=9)
+    gd = pkg.synth.make_graph("tiny", seed=9).to(dev)
+    counts = {nt: int(g[nt].num_nodes) for nt in g.node_types}
+    ets = list(g.edge_types)
+    sd = R.init_state(counts, ets, seed=5)
+    cfg = {"model": {"architecture": "RGCN", "hidden_dim": 128, "num_layers": 2, "dropout": 0.2, "use_batch_norm": True,
+                     "activation": "relu"}}
+    model = M.build_model(cfg, (g.node_types, g.edge_types), None).to(dev)
+    model._init_embeddings(gd)
+    model.load_state_dict(sd)
+    model.train()
+    ei = g["patient", "has_lab", "lab"].edge_index
+    tgt = g["patient", "has_lab", "lab"].edge_attr.squeeze(-1)
+    pi, li = ei[0], ei[1]
+    torch.manual_seed(77)
+    pred = model.predict_lab_values(gd, pi.to(dev), li.to(dev))
+    streams = model._last_streams
+    tags = dict(streams.log)
+    assert "init.enc.drop0" in tags and "fwd.enc.drop0" in tags and "edge_predictor.drop1" in tags
+
+    def mask_fn(tag, x):
+        return ops.dropout_mask(x.numel(), 0.2, streams.seed, tags[tag], dev).cpu().view_as(x).to(x.dtype)
+
+    sd_ref = {k: v.clone() for k, v in sd.items()}
+    ref = R.predict_lab_values(sd_ref, counts, ets, g.edge_index_dict, pi, li, True, 0.2, mask_fn=mask_fn)
+    assert relerr(pred, ref) <= 1e-4
+    after = model.state_dict()
+    for k in ("patient_transform.1.running_mean", "patient_transform.5.running_var", "batch_norms.1.lab.running_var"):
+        assert relerr(after[k], sd_ref[k]) <= 1e-5, k
+    assert int(after["patient_transform.1.num_batches_tracked"]) == 2
+    # statistical check of the drop rate on a large site
+    mk = ops.dropout_mask(1 << 22, 0.2, 99, 0, dev)
+    assert abs(float((mk == 0).float().mean()) - 0.2) < 2e-3
+
+
+def test_trainer_tracks_oracle_adam(dev):
+    """5 optimizer steps (mse + lab weights): the CUDA Trainer vs oracle + torch.optim.Adam on the CPU."""
+    pkg, G, ops, M, T, L = _mods()
+    g = pkg.synth.make_graph("tiny", seed=4)
+    counts = {nt: int(g[nt].num_nodes) for nt in g.node_types}
+    ets = list(g.edge_types)
+    sd = R.init_state(counts, ets, seed=8)
+    cfg = {"model": {"architecture": "RGCN", "hidden_dim": 128, "num_layers": 2, "dropout": 0.0, "use_batch_norm": True,
+                     "activation": "relu"},
+           "train": {"loss": "mse", "epochs": 5, "early_stopping_patience": 15, "optimizer": {"type": "adam", "lr": 1e-3,
+                     "weight_decay": 1e-5}, "lr_scheduler": {"enabled": True, "type": "reduce_on_plateau"}}}
+    model = M.build_model(cfg, (g.node_types, g.edge_types), None)
+    masker = T.EdgeMasker(pkg.synth.make_graph("tiny", seed=4), 0.7, 0.15, 0.15, 0.2, 42)
+    for m_, ref_m in zip((masker.train_mask, masker.val_mask, masker.test_mask), R.split_masks(masker.num_edges)):
+        assert torch.equal(m_, ref_m)                                          # bit-exact splits
+    trainer = T.Trainer(model, masker.data, masker, cfg, dev)                  # optimizer built before tables exist (N2)
+    model._init_embeddings(trainer.data)
+    model.load_state_dict(sd)
+    assert sum(p.numel() for grp in trainer.optimizer.param_groups for p in grp["params"]) == 483970
+
+    ei = g["patient", "has_lab", "lab"].edge_index
+    attr = g["patient", "has_lab", "lab"].edge_attr
+    tr = masker.train_mask
+    pi, li, tgt = ei[0][tr], ei[1][tr], attr[tr].squeeze(-1)
+    w = R.lab_weights(li, tgt, counts["lab"])
+    torch.testing.assert_close(trainer.lab_weights.cpu(), w, rtol=1e-5, atol=1e-7)
+    sd_ref = {k: v.clone() for k, v in sd.items()}
+    keys = R.trainable_keys(sd_ref)
+    params = [sd_ref[k].requires_grad_(True) for k in keys]
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-5)
+    for step in range(5):
+        loss_gpu = trainer.train_epoch(seed=1000 + step)
+        sup = R.supervision_mask(int(tr.sum()), 0.2, 1000 + step)
+        opt.zero_grad()
+        pred = R.predict_lab_values(sd_ref, counts, ets, g.edge_index_dict, pi, li, True, p_drop=0.0)
+        loss = R.weighted_loss(pred, tgt, li, w, sup, "mse")
+        loss.backward()
+        opt.step()
+        assert abs(loss_gpu - float(loss)) <= 1e-3 * abs(float(loss)), (step, loss_gpu, float(loss))
+    val_gpu = trainer.validate("val")
+    va = masker.val_mask
+    with torch.no_grad():
+        pv = R.predict_lab_values({k: v.detach() for k, v in sd_ref.items()}, counts, ets, g.edge_index_dict, ei[0][va], ei[1][va], False)
+        val_ref = float(R.regression_loss(pv, attr[va].squeeze(-1), "mse"))
+    assert abs(val_gpu - val_ref) <= 2e-3 * abs(val_ref)
+
+
+def test_model_rejects_cpu_and_bad_config(dev):
+    pkg, G, ops, M, T, L = _mods()
+    cfg = {"model": {"architecture": "RGCN", "hidden_dim": 128, "num_layers": 2, "dropout": 0.2, "use_batch_norm": True,
+                     "activation": "relu"}}
+    md = (pkg.synth.NODE_TYPES, pkg.synth.EDGE_TYPES)
+    model = M.build_model(cfg, md, None)
+    g = pkg.synth.make_graph("tiny")
+    with pytest.raises(RuntimeError):
+        model(g)                                             # CPU module: no CPU path
+    with pytest.raises(ValueError):
+        M.build_model({"model": dict(cfg["model"], architecture="nope")}, md, None)
+    with pytest.raises(ValueError):
+        M.build_model({"model": dict(cfg["model"], activation="nope")}, md, None)
+    # reference smoke (model.py:619-660): hidden 64, edge_predictor on a [10, 128] tensor
+    m64 = M.HeteroRGCN(metadata=md, hidden_dim=64, num_layers=2, dropout=0.2, patient_feature_dim=3).to(dev)
+    m64.eval()
+    out = m64.edge_predictor(torch.randn(10, 128, device=dev))
+    assert tuple(out.shape) == (10, 1)
+    # PyG >= 2.4 key format is accepted on load
+    model = model.to(dev)
+    model._init_embeddings(g)
+    sd = {k.replace("patient__has_lab__lab", "<patient___has_lab___lab>"): v for k, v in model.state_dict().items()}
+    model.load_state_dict(sd)

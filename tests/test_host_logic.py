@@ -1,0 +1,85 @@
+"""CPU: host-side logic of the product that needs no GPU -- synthetic graph contract, EdgeMasker bit-exactness
+with the reference's split arithmetic, lab weights, model construction / state_dict layout."""
+import importlib
+
+import pytest
+import torch
+
+from oracle import hetero_rgcn_ref as R
+
+PKG = "multi-modal-gnn_b200"
+
+
+def test_synthetic_graph_contract(pkg):
+    g = pkg.synth.make_graph("C1")
+    assert g.node_types == ["patient", "lab", "diagnosis", "medication"]
+    assert [et[1] for et in g.edge_types] == ["has_lab", "has_lab_rev", "has_diagnosis", "has_diagnosis_rev",
+                                              "has_medication", "has_medication_rev"]
+    for fwd, rev in zip(g.edge_types[::2], g.edge_types[1::2]):
+        assert torch.equal(g[fwd].edge_index.flip(0), g[rev].edge_index)
+        ei = g[fwd].edge_index
+        key = ei[0] * 100000 + ei[1]
+        assert key.unique().numel() == key.numel(), "pairs must be unique"
+        assert ei.dtype == torch.int64
+    ei = g["patient", "has_lab", "lab"].edge_index
+    k = ei[1] * 1834 + ei[0]
+    assert bool((k[1:] > k[:-1]).all()), "has_lab is grouped by lab, then patient"
+    ea = g["patient", "has_lab", "lab"].edge_attr
+    assert ea.shape == (61484, 1) and ea.dtype == torch.float32 and float(ea.abs().max()) <= 5.0
+    assert "edge_attr" not in g["patient", "has_diagnosis", "diagnosis"]
+    g2 = pkg.synth.make_graph("C1")
+    assert torch.equal(g2["patient", "has_lab", "lab"].edge_index, ei), "generator must be deterministic"
+    deg = torch.bincount(ei[0], minlength=1834)
+    assert int((deg < 6).sum()) > 0 and int(deg.min()) >= 1
+
+
+def test_edge_masker_matches_reference_split_arithmetic(pkg, golden_c1):
+    T = importlib.import_module(PKG + ".trainer")
+    g = pkg.synth.make_graph("C1")
+    masker = T.EdgeMasker(g, 0.7, 0.15, 0.15, 0.2, 42)
+    sp = golden_c1["split"]                      # produced by the unmodified reference EdgeMasker
+    assert torch.equal(masker.train_mask, sp["train"]) and torch.equal(masker.val_mask, sp["val"])
+    assert torch.equal(masker.test_mask, sp["test"])
+    assert (int(masker.train_mask.sum()), int(masker.val_mask.sum()), int(masker.test_mask.sum())) == (43038, 9222, 9224)
+    sup = masker.supervision_mask("train", seed=golden_c1["sup_seed"])
+    assert torch.equal(sup, golden_c1["sup_mask"])
+    assert bool(masker.supervision_mask("val").all())
+    with pytest.raises(ValueError):
+        masker.split_mask("nope")
+    ei, ev, mask, s = masker.get_masked_data("val")
+    assert ei.shape == (2, 9222) and ev.shape == (9222,) and mask is masker.val_mask
+    with pytest.raises(AssertionError):
+        T.EdgeMasker(g, 0.7, 0.2, 0.2)
+
+
+def test_lab_weights_match_reference(pkg, golden_c1):
+    T = importlib.import_module(PKG + ".trainer")
+    g = pkg.synth.make_graph("C1")
+    ei = g["patient", "has_lab", "lab"].edge_index
+    ea = g["patient", "has_lab", "lab"].edge_attr
+    tr = golden_c1["split"]["train"]
+    w = T.compute_lab_weights(ei[1][tr], ea[tr].squeeze(-1), 50)
+    torch.testing.assert_close(w, golden_c1["lab_weights"], rtol=1e-5, atol=1e-7)
+    assert abs(float(w.sum()) - 50.0) < 1e-3
+    # a lab with a single sample gets variance 1 (train.py:313-319)
+    w2 = T.compute_lab_weights(torch.tensor([0, 0, 0, 1]), torch.tensor([1.0, 2.0, 4.0, 9.0]), 3)
+    ref = R.lab_weights(torch.tensor([0, 0, 0, 1]), torch.tensor([1.0, 2.0, 4.0, 9.0]), 3)
+    torch.testing.assert_close(w2, ref, rtol=1e-6, atol=1e-7)
+
+
+def test_model_state_dict_layout(pkg, golden_c1):
+    M = importlib.import_module(PKG + ".model")
+    cfg = {"model": {"architecture": "RGCN", "hidden_dim": 128, "num_layers": 2, "dropout": 0.2, "use_batch_norm": True,
+                     "activation": "relu"}}
+    model = M.build_model(cfg, (pkg.synth.NODE_TYPES, pkg.synth.EDGE_TYPES), None)
+    assert sum(p.numel() for p in model.parameters()) == 483970               # KA-1, before the lazy tables exist
+    assert model.degree_threshold == 6 and model.hidden_dim == 128 and model.num_layers == 2 and model.dropout == 0.2
+    g = pkg.synth.make_graph("C1")
+    model._init_embeddings(g)
+    model._init_embeddings(g)                                                  # idempotent
+    assert sum(p.numel() for p in model.parameters()) == 752514
+    assert list(model.state_dict().keys()) == golden_c1["state_keys"]          # the reference's 108 keys, same order
+    model.load_state_dict(golden_c1["state_before"])
+    assert model.embeddings["lab"].weight.shape == (50, 128)
+    with pytest.raises(NotImplementedError):
+        M.build_model({"model": dict(cfg["model"], architecture="HGT")}, (pkg.synth.NODE_TYPES, pkg.synth.EDGE_TYPES), None)
