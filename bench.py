@@ -128,7 +128,7 @@ class ClockSampler:
     def start(self):
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -161,7 +161,9 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            busy = [c for c, m in zip(sm, mx) if c >= 0.4 * m] or sm          # samples taken while the GPU was clocked up
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm), "samples_under_load": len(busy)}
         return out
 
 
@@ -225,15 +227,15 @@ def run_ours(args):
         return loss
 
     model.train()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()          # sampled over warm-up + both timed regions (nvidia-smi needs ~1 s to produce its first line)
     # ---- warm-up ----
     for i in range(args.warmup):
         step_device(i)
     torch.cuda.synchronize()
 
     # ---- timed: device-resident inputs ----
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -255,7 +257,6 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / args.steps
-    clk = clocks.stop() if rank == 0 else None
     final_loss = float(loss.item())
 
     # ---- timed: end to end through the public Trainer API with host inputs ----
@@ -263,7 +264,7 @@ def run_ours(args):
     pi_d, li_d, ev_d = torch.empty_like(pi), torch.empty_like(li), torch.empty_like(ev)
     sup_d = torch.empty(n_train, dtype=torch.bool, device=dev)
     h2d = pi_h.numel() * 8 + li_h.numel() * 8 + ev_h.numel() * 4 + n_train
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, args.steps)
 
     def step_e2e(i):
         pi_d.copy_(pi_h, non_blocking=True); li_d.copy_(li_h, non_blocking=True)
@@ -283,6 +284,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t.item()) * 1e3 / e2e_steps
+    clk = clocks.stop() if rank == 0 else None
 
     # ---- one instrumented step: per-kernel CUDA-event durations -> dominant kernel + roofline ----
     roof, kernels = None, None
@@ -339,7 +341,7 @@ def a_share(ms, tot):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
