@@ -171,7 +171,28 @@ int b2g_l2norm_bwd(const float* y, const float* dy, const float* inv_norm, int64
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * (e) loss -- train.py:364-386 weighted MAE / MSE over the supervised subset, model.py:602-605
+ * (e) fused edge decoder -- EdgeRegressionHead([64,32]) over (patient, lab) pairs, model.py:305-333,373-386
+ * ---------------------------------------------------------------------------------------------- */
+/* pred[i] = w3 . drop(relu(W2 drop(relu(U[pi[i]] + V[li[i]])) + b2)) + b3
+ *   U [N_p,64] = h_patient W1[:, :d]^T, V [N_l,64] = h_lab W1[:, d:]^T + b1 (first layer factorised per node, so the
+ *   [M, 2d] concatenation of model.py:319-333 is never built); W2 [32,64], b2 [32], w3 [32], b3 [1].
+ * Dropout masks: Philox(seed, sid1) over the flat [M,64] layer-1 output, (seed, sid2) over the flat [M,32] one. */
+int b2g_decoder_fwd(const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2,
+                    const float* b2, const float* w3, const float* b3, int64_t m, float p_drop, uint64_t seed,
+                    uint64_t sid1, uint64_t sid2, float* pred, void* stream);
+/* Backward of the above for upstream gradient dpred[M].  Pairs with dpred == 0 (the unsupervised 80 %,
+ * train.py:366-368) are compacted away first (stable order -> deterministic sums).  Outputs: g_rows[M,64] = d loss /
+ * d (U[p]+V[l]) written ONLY for pairs with dpred != 0; active_flags[M] = 1.0 / 0.0 marks those rows (pass it as
+ * col_scale to b2g_gather_reduce* to form dU / dV without touching unwritten rows); dW2 [32,64], db2 [32], dw3 [32],
+ * db3 [1].  ws: b2g_decoder_bwd_ws_bytes(m). */
+size_t b2g_decoder_bwd_ws_bytes(int64_t m);
+int b2g_decoder_bwd(const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2,
+                    const float* b2, const float* w3, const float* dpred, int64_t m, float p_drop, uint64_t seed,
+                    uint64_t sid1, uint64_t sid2, float* g_rows, float* active_flags, float* dW2, float* db2,
+                    float* dw3, float* db3, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (f) loss -- train.py:364-386 weighted MAE / MSE over the supervised subset, model.py:602-605
  * ---------------------------------------------------------------------------------------------- */
 /* loss = (1/n_sup) * sum_{i: sup[i]} w[lab[i]] * (|p-t| or (p-t)^2); grad[i] = dloss/dpred[i] (0 where
  * !sup[i]).  sup / w may be NULL (all edges, unit weights).  kind: 0 = mae, 1 = mse, 2 = huber(delta 1).

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb2g.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["graph.cu", "spmm.cu", "dense.cu", "norm.cu"]
+SOURCES = ["graph.cu", "spmm.cu", "dense.cu", "norm.cu", "decoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -107,6 +107,10 @@ _PROTOS = {
     "b2g_dropout_mask": (c_int, [c_int64, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_l2norm_fwd": (c_int, [_P, c_int64, c_int, c_float, _P, _P, _P]),
     "b2g_l2norm_bwd": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
+    "b2g_decoder_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, c_uint64, _P, _P]),
+    "b2g_decoder_bwd_ws_bytes": (c_size_t, [c_int64]),
+    "b2g_decoder_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, c_uint64, _P, _P, _P, _P,
+                                _P, _P, _P, c_size_t, _P]),
     "b2g_loss_ws_bytes": (c_size_t, [c_int64]),
     "b2g_weighted_loss": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
 }

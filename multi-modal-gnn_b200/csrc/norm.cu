@@ -7,7 +7,7 @@
 namespace {
 using namespace b2g;
 
-constexpr int MAX_PARTIALS = 592;  // 4 x 148 CTAs
+constexpr int MAX_PARTIALS = 296;  // 2 x 148 CTAs
 
 // activation codes (model.py:145-153): 0 none, 1 relu, 2 leaky_relu(0.01), 3 elu(alpha 1)
 __device__ __forceinline__ float act_fwd(float v, int act) {
@@ -84,17 +84,38 @@ __global__ void __launch_bounds__(256) k_col_partial(const float* __restrict__ x
   }
 }
 
-// stage 2 of MODE 0: mean / rstd (+ running-stat update like nn.BatchNorm1d in training mode)
-__global__ void k_bn_finalize(const double* __restrict__ partial, int n_part, int64_t m, int d, float eps, float momentum,
-                              float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
-                              float* __restrict__ running_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
-  double s0 = 0, s1 = 0;
-  for (int p = 0; p < n_part; ++p) {
-    s0 += partial[((size_t)p * 2 + 0) * d + c];
-    s1 += partial[((size_t)p * 2 + 1) * d + c];
+// deterministic column totals of the per-CTA partials: 32 columns x 8 slices per block, slices combined in fixed order
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partial, int n_part, int d, int c, int slice, double& s0,
+                                                double& s1) {
+  __shared__ double sh[2][8][32];
+  double a0 = 0, a1 = 0;
+  if (c < d) {
+    for (int p = slice; p < n_part; p += 8) {
+      a0 += partial[((size_t)p * 2 + 0) * d + c];
+      a1 += partial[((size_t)p * 2 + 1) * d + c];
+    }
   }
+  sh[0][slice][threadIdx.x & 31] = a0;
+  sh[1][slice][threadIdx.x & 31] = a1;
+  __syncthreads();
+  s0 = s1 = 0;
+  if (slice == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s0 += sh[0][k][threadIdx.x & 31];
+      s1 += sh[1][k][threadIdx.x & 31];
+    }
+  }
+}
+
+// stage 2 of MODE 0: mean / rstd (+ running-stat update like nn.BatchNorm1d in training mode); block = 256 threads
+__global__ void __launch_bounds__(256) k_bn_finalize(const double* __restrict__ partial, int n_part, int64_t m, int d, float eps, float momentum,
+                                                     float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
+                                                     float* __restrict__ running_var) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  double s0, s1;
+  reduce_partials(partial, n_part, d, c, slice, s0, s1);
+  if (slice != 0 || c >= d) return;
   double mu = s0 / (double)m;
   double var = s1 / (double)m - mu * mu;
   if (var < 0) var = 0;
@@ -108,15 +129,12 @@ __global__ void k_bn_finalize(const double* __restrict__ partial, int n_part, in
 }
 
 // stage 2 of MODE 1: totals -> sums[2][d] (double) and dbeta / dgamma
-__global__ void k_bn_bwd_finalize(const double* __restrict__ partial, int n_part, int d, double* __restrict__ sums, float* __restrict__ dgamma,
-                                  float* __restrict__ dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
-  double s0 = 0, s1 = 0;
-  for (int p = 0; p < n_part; ++p) {
-    s0 += partial[((size_t)p * 2 + 0) * d + c];
-    s1 += partial[((size_t)p * 2 + 1) * d + c];
-  }
+__global__ void __launch_bounds__(256) k_bn_bwd_finalize(const double* __restrict__ partial, int n_part, int d, double* __restrict__ sums,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  double s0, s1;
+  reduce_partials(partial, n_part, d, c, slice, s0, s1);
+  if (slice != 0 || c >= d) return;
   sums[c] = s0;
   sums[d + c] = s1;
   if (dbeta) dbeta[c] = (float)s0;
@@ -379,7 +397,7 @@ extern "C" int b2g_bn_stats(const float* x, int64_t m, int d, float eps, float m
   size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
   k_col_partial<0><<<parts, 256, smem, st>>>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, partial);
   B2G_LAUNCH_CHECK();
-  k_bn_finalize<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(partial, parts, m, d, eps, momentum, mean, rstd, running_mean, running_var);
+  k_bn_finalize<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, m, d, eps, momentum, mean, rstd, running_mean, running_var);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }
@@ -421,7 +439,7 @@ extern "C" int b2g_bn_bwd(const float* x, const float* dy, int64_t m, int d, con
   size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
   k_col_partial<1><<<parts, 256, smem, st>>>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, partial);
   B2G_LAUNCH_CHECK();
-  k_bn_bwd_finalize<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(partial, parts, d, sums, dgamma, dbeta);
+  k_bn_bwd_finalize<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, d, sums, dgamma, dbeta);
   B2G_LAUNCH_CHECK();
   int64_t n4 = m * d / 4;
   k_bn_bwd_apply<<<ew_grid(n4), 256, 0, st>>>(x, dy, n4, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, batch_stats, sums, dx);

@@ -24,11 +24,12 @@ __device__ __forceinline__ void reduce_span(const b2g_rel_t& rel, int b, int e, 
           c3 = __shfl_sync(FULL, my, t + 3);
       float s0 = __shfl_sync(FULL, cs, t), s1 = __shfl_sync(FULL, cs, t + 1), s2 = __shfl_sync(FULL, cs, t + 2),
             s3 = __shfl_sync(FULL, cs, t + 3);
+      // a zero column scale means "row not present" (e.g. decoder gradient rows of unsupervised pairs): never read it
       RowVec<D> r0, r1, r2, r3;
-      r0.load(rel.x + (size_t)c0 * D, lane);
-      r1.load(rel.x + (size_t)c1 * D, lane);
-      r2.load(rel.x + (size_t)c2 * D, lane);
-      r3.load(rel.x + (size_t)c3 * D, lane);
+      if (s0 != 0.f) r0.load(rel.x + (size_t)c0 * D, lane); else r0.zero();
+      if (s1 != 0.f) r1.load(rel.x + (size_t)c1 * D, lane); else r1.zero();
+      if (s2 != 0.f) r2.load(rel.x + (size_t)c2 * D, lane); else r2.zero();
+      if (s3 != 0.f) r3.load(rel.x + (size_t)c3 * D, lane); else r3.zero();
       acc.fma(s0, r0);
       acc.fma(s1, r1);
       acc.fma(s2, r2);
@@ -38,7 +39,7 @@ __device__ __forceinline__ void reduce_span(const b2g_rel_t& rel, int b, int e, 
       int c = __shfl_sync(FULL, my, t);
       float s = __shfl_sync(FULL, cs, t);
       RowVec<D> r;
-      r.load(rel.x + (size_t)c * D, lane);
+      if (s != 0.f) r.load(rel.x + (size_t)c * D, lane); else r.zero();
       acc.fma(s, r);
     }
   }

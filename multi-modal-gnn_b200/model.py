@@ -75,6 +75,7 @@ class EdgeRegressionHead(nn.Module):
         layers.append(nn.Linear(prev, output_dim))
         self.mlp = nn.Sequential(*layers)
         self.dropout_p = float(dropout)
+        self.fused = True     # hidden_dims == [64, 32] (the reference's hard-coded shape) -> csrc/decoder.cu
 
     def _linears(self):
         return [m for m in self.mlp if isinstance(m, nn.Linear)]
@@ -109,6 +110,12 @@ class EdgeRegressionHead(nn.Module):
         w0 = lins[0].weight
         u = ops.linear(h_p, w0[:, :d].contiguous(), None)
         v = ops.linear(h_l, w0[:, d:].contiguous(), lins[0].bias)
+        if len(lins) == 3 and lins[1].weight.shape == (32, 64) and lins[2].weight.shape == (1, 32) and self.fused:
+            drop = self.training and self.dropout_p > 0
+            sid1 = streams.take(f"{tag}.drop0") if drop else 0
+            sid2 = streams.take(f"{tag}.drop1") if drop else 0
+            return ops.DecoderHeadFn.apply(u, v, lins[1].weight, lins[1].bias, lins[2].weight, lins[2].bias, pairs,
+                                           self.dropout_p, streams.seed, sid1, sid2, self.training)
         z = ops.PairAddReluFn.apply(u, v, pairs)
         out = self._tail(z, lins[1:], streams, tag, relu_done=True)
         return out.squeeze(-1)

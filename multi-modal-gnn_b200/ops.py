@@ -442,6 +442,53 @@ class PairAddReluFn(Function):
         return du, dv, None
 
 
+class DecoderHeadFn(Function):
+    """EdgeRegressionHead([64, 32]) over a pair list in one kernel each way (csrc/decoder.cu):
+    pred = w3 . drop(relu(W2 drop(relu(U[p] + V[l])) + b2)) + b3   (model.py:305-333,373-386)."""
+
+    @staticmethod
+    def forward(ctx, u, v, w2, b2, w3, b3, pairs: PairIndex, p_drop, seed, sid1, sid2, training):
+        lib = _lib.load()
+        u, v, w2, b2, w3, b3 = (_f32(t, n) for t, n in ((u, "U"), (v, "V"), (w2, "W2"), (b2, "b2"), (w3, "w3"), (b3, "b3")))
+        if u.shape[1] != 64 or w2.shape != (32, 64) or w3.numel() != 32:
+            raise _lib.B2GError("fused decoder supports hidden_dims [64, 32] only")
+        p = float(p_drop) if training else 0.0
+        pred = torch.empty(pairs.m, dtype=torch.float32, device=u.device)
+        cost(pairs.m * (16 + 4 + 256) + 4 * v.numel(), 2 * pairs.m * (64 * 32 + 32 + 64))
+        _run("b2g_decoder_fwd", lib.b2g_decoder_fwd, u.data_ptr(), v.data_ptr(), pairs.patient_idx.data_ptr(), pairs.lab_idx.data_ptr(),
+             w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), pairs.m, p, int(seed), int(sid1), int(sid2), pred.data_ptr(),
+             _stream())
+        ctx.save_for_backward(u, v, w2, b2, w3)
+        ctx.meta = (pairs, p, int(seed), int(sid1), int(sid2))
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        lib = _lib.load()
+        u, v, w2, b2, w3 = ctx.saved_tensors
+        pairs, p, seed, sid1, sid2 = ctx.meta
+        dpred = _f32(dpred, "grad")
+        dev = u.device
+        m = pairs.m
+        g = torch.empty((m, 64), dtype=torch.float32, device=dev)
+        flags = torch.empty(m, dtype=torch.float32, device=dev)
+        dw2, db2, dw3 = torch.empty_like(w2), torch.empty_like(b2), torch.empty_like(w3)
+        db3 = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = workspace(lib.b2g_decoder_bwd_ws_bytes(m), dev)
+        cost(m * (16 + 4 + 4) + m // 5 * 512, 2 * (m // 5) * 3 * 64 * 32)
+        _run("b2g_decoder_bwd", lib.b2g_decoder_bwd, u.data_ptr(), v.data_ptr(), pairs.patient_idx.data_ptr(), pairs.lab_idx.data_ptr(),
+             w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), dpred.data_ptr(), m, p, seed, sid1, sid2, g.data_ptr(), flags.data_ptr(),
+             dw2.data_ptr(), db2.data_ptr(), dw3.data_ptr(), db3.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        du = dv = None
+        if ctx.needs_input_grad[0]:
+            du = torch.empty_like(u)
+            gather_reduce_([pairs.by_patient], [g], [None], [flags], du, False)
+        if ctx.needs_input_grad[1]:
+            dv = torch.empty_like(v)
+            gather_reduce_([pairs.by_lab], [g], [None], [flags], dv, False)
+        return du, dv, dw2, db2, dw3.view_as(w3), db3, None, None, None, None, None, None
+
+
 class GatherRowsFn(Function):
     """table[idx]  (nn.Embedding lookup, model.py:225-226, for index sets other than arange)."""
 

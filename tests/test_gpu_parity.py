@@ -478,3 +478,55 @@ def test_model_rejects_cpu_and_bad_config(dev):
     model._init_embeddings(g)
     sd = {k.replace("patient__has_lab__lab", "<patient___has_lab___lab>"): v for k, v in model.state_dict().items()}
     model.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("m,p_drop,frac_active", [(1, 0.0, 1.0), (257, 0.0, 1.0), (5000, 0.0, 0.2), (43038, 0.2, 0.2), (3000, 0.2, 0.0)])
+def test_fused_decoder_matches_oracle_head(m, p_drop, frac_active, dev):
+    """csrc/decoder.cu vs the oracle's EdgeRegressionHead on cat([h_p[pi], h_l[li]]) incl. replayed dropout masks and a
+    sparse upstream gradient (only 'supervised' pairs carry gradient, as in train.py:366-368)."""
+    pkg, G, ops, M, T, L = _mods()
+    gen = torch.Generator().manual_seed(m)
+    n_p, n_l, d = 700, 37, 128
+    hp, hl = torch.randn(n_p, d, generator=gen), torch.randn(n_l, d, generator=gen)
+    pi, li = torch.randint(0, n_p, (m,), generator=gen), torch.randint(0, n_l, (m,), generator=gen)
+    head = M.EdgeRegressionHead(2 * d, [64, 32], 1, p_drop).to(dev)
+    head.train()
+    sd = {"h.mlp." + k.split("mlp.")[1]: v.detach().cpu().clone() for k, v in head.state_dict().items()}
+    go = torch.randn(m, generator=gen) * (torch.rand(m, generator=gen) < frac_active)
+    pairs = G.PairIndex(pi.to(dev), li.to(dev), n_p, n_l)
+    streams = M._DropoutStreams(p_drop > 0)
+    hpd, hld = hp.to(dev).requires_grad_(True), hl.to(dev).requires_grad_(True)
+    pred = head.forward_pairs(hpd, hld, pairs, streams, "h")
+    pred.backward(go.to(dev))
+    tags = dict(streams.log)
+
+    def mask_fn(tag, x):
+        return ops.dropout_mask(x.numel(), p_drop, streams.seed, tags[tag], dev).cpu().view_as(x).to(x.dtype)
+
+    sdr = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    hpr, hlr = hp.double().requires_grad_(True), hl.double().requires_grad_(True)
+    ref = R.edge_head(sdr, "h", torch.cat([hpr[pi], hlr[li]], 1), True, p_drop, mask_fn if p_drop > 0 else None)
+    ref.backward(go.double())
+    assert relerr(pred, ref) <= 2e-5
+    if frac_active > 0:
+        assert relerr(hpd.grad, hpr.grad) <= 1e-4 and relerr(hld.grad, hlr.grad) <= 1e-4
+        for name, prm in head.named_parameters():
+            assert relerr(prm.grad, sdr["h." + name].grad) <= 1e-4, name
+    else:
+        assert float(hpd.grad.abs().max()) == 0.0 and float(head.mlp[3].weight.grad.abs().max()) == 0.0
+    # the unfused composition (generic kernels) computes the same function
+    head.fused = False
+    hp2, hl2 = hp.to(dev).requires_grad_(True), hl.to(dev).requires_grad_(True)
+    streams2 = M._DropoutStreams(False)
+    streams2.seed = streams.seed
+    pred2 = head.forward_pairs(hp2, hl2, pairs, streams2, "h")
+    assert relerr(pred2, pred) <= 1e-5
+    # determinism
+    head.fused = True
+    head.zero_grad()
+    hp3, hl3 = hp.to(dev).requires_grad_(True), hl.to(dev).requires_grad_(True)
+    s3 = M._DropoutStreams(False)
+    s3.seed = streams.seed
+    p3 = head.forward_pairs(hp3, hl3, pairs, s3, "h")
+    p3.backward(go.to(dev))
+    assert torch.equal(p3, pred) and torch.equal(hp3.grad, hpd.grad)
