@@ -315,7 +315,8 @@ def run_ours(args):
         edges_per_step = NUM_LAYERS * spec.directed_edges_per_layer * world
         line = {"metric": METRIC, "value": edges_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": "f32 (large-M linears: TF32 operands on tcgen05, fp32 accumulate)" if ops.PRECISION == "tf32" else "f32",
+                "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {spec.n_patient} patients/{spec.n_lab} labs/{spec.n_dx} dx/{spec.n_med} meds, "
                                        f"{spec.e_lab}/{spec.e_dx}/{spec.e_med} edges per GPU, d=128, L=2, dropout 0.2, mse + lab weights, "
                                        f"{n_train} train pairs, 20% supervised, Adam",

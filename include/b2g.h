@@ -132,6 +132,16 @@ size_t b2g_linear_bwd_weight_ws_bytes(int64_t m, int n, int k);
 int b2g_linear_bwd_weight(const float* dy, const float* x, int64_t m, int n, int k, float* dw, float* db,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* Same product on the tcgen05 tensor cores: fp32 operands consumed as TF32 (kind::tf32), fp32 accumulation in TMEM,
+ * fp32 output; TMA (cp.async.bulk.tensor, 128-byte swizzle) stages X tiles and keeps W resident in shared memory.
+ * Relative error ~1e-3 (north_star tolerance for tensor-core GEMM outputs: 1e-2).  _supported() says whether
+ * (m, n, k) fits: n % 32 == 0, n <= 256, k % 32 == 0, W + at least one X stage within 227 KB of shared memory.
+ * dx = dy W is the same call on W^T (b2g_transpose). */
+int b2g_linear_fwd_tc_supported(int64_t m, int n, int k);
+int b2g_linear_fwd_tc(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y,
+                      int accumulate, void* stream);
+int b2g_transpose(const float* in, int rows, int cols, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (d') BatchNorm1d + ReLU + Dropout, row L2 normalisation (model.py:93-105,134-139,259-269)
  * ---------------------------------------------------------------------------------------------- */

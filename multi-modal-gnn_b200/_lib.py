@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb2g.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["graph.cu", "spmm.cu", "dense.cu", "norm.cu", "decoder.cu"]
+SOURCES = ["graph.cu", "spmm.cu", "dense.cu", "norm.cu", "decoder.cu", "dense_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -93,6 +93,9 @@ _PROTOS = {
     "b2g_scatter_values": (c_int, [_P, _P, c_int64, _P, _P]),
     "b2g_gather_values": (c_int, [_P, _P, c_int64, _P, _P]),
     "b2g_linear_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
+    "b2g_linear_fwd_tc_supported": (c_int, [c_int64, c_int, c_int]),
+    "b2g_linear_fwd_tc": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
+    "b2g_transpose": (c_int, [_P, c_int, c_int, _P, _P]),
     "b2g_linear_bwd_input": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
     "b2g_linear_bwd_weight_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "b2g_linear_bwd_weight": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),

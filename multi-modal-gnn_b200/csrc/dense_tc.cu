@@ -1,0 +1,348 @@
+// tcgen05 (5th-gen tensor core) dense layer for the large-M linears:  Y[M,N] = X[M,K] W[N,K]^T (+ bias)
+// (nn.Linear / SAGEConv.lin_r on the patient rows, model.py:93-103,125-131).
+//
+// fp32 operands are fed to the tensor cores as TF32 (kind::tf32: the MMA reads the fp32 words in shared memory
+// and ignores the low 13 mantissa bits), accumulation is fp32 in TMEM, output is fp32.  No conversion pass and no
+// extra HBM traffic: the kernel is a stream over X and Y (1 KB per row for d = 128), i.e. HBM / L2 bound.
+//
+// Persistent, warp-specialised CTA (256 threads), one 128-row tile of X at a time:
+//   warp 0   TMA producer: W once (resident for the CTA's lifetime), then X tiles into a 2-stage ring
+//            (cp.async.bulk.tensor, SWIZZLE_128B boxes of 32 floats x 128 rows)
+//   warp 1   MMA issuer: one elected lane issues K/8 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=256, K=8 each)
+//            per tile into one of two TMEM accumulators; tcgen05.commit releases the smem stage and
+//            publishes the accumulator
+//   warp 2   TMEM allocator / deallocator
+//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> + bias (+ previous Y when accumulating) -> 128-bit stores
+#include <cuda.h>
+#include "common.cuh"
+
+namespace {
+using namespace b2g;
+
+constexpr int TC_THREADS = 256;
+constexpr int TILE_M = 128;
+constexpr int KB = 32;                          // floats per 128-byte swizzle row
+constexpr int SUB_BYTES = TILE_M * KB * 4;      // one [128 rows x 128 B] sub-tile of X = 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
+// LBO (unused for swizzled K-major) in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48),
+// layout type SWIZZLE_128B (= 2) in [61,64).  The tile base must be 1024-byte aligned (base_offset = 0).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10)/[10,13), K-major A and B
+// (bits 15,16 = 0), N >> 3 in [17,23), M >> 4 in [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+struct TcParams {
+  const float* bias;   // [N] or null
+  float* y;            // [M, N]
+  int64_t m;
+  int n, k;
+  int accumulate;
+  int tmem_cols;       // 2 * N rounded to a power of two >= 32
+  int stages;          // X ring depth: 2 when it fits in shared memory, else 1
+};
+
+// dynamic smem layout (1024-byte aligned): W sub-tiles [K/32][N rows x 128 B] | X stages [2][K/32][128 rows x 128 B]
+__global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_constant__ CUtensorMap map_x,
+                                                               const __grid_constant__ CUtensorMap map_w, TcParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_w, bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = prm.k / KB;
+  const uint32_t w_bytes = (uint32_t)prm.n * prm.k * 4;
+  const uint32_t x_bytes = (uint32_t)TILE_M * prm.k * 4;
+  // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window
+  uint8_t* smem_w = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  uint8_t* smem_x = smem_w + w_bytes;
+  const int64_t n_tiles = (prm.m + TILE_M - 1) / TILE_M;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_w, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_tfull[s], 1);
+      mbar_init(&bar_tempty[s], 4);      // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(prm.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      mbar_expect_tx(&bar_w, w_bytes);
+      for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(smem_w + (size_t)kb * prm.n * KB * 4, &map_w, &bar_w, kb * KB, 0);
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int s = it % prm.stages;
+        const uint32_t ph = (it / prm.stages) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);              // first use of each stage passes immediately
+        mbar_expect_tx(&bar_full[s], x_bytes);
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_2d(smem_x + (size_t)s * x_bytes + (size_t)kb * SUB_BYTES, &map_x, &bar_full[s], kb * KB, (int)(t * TILE_M));
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc(prm.n);
+    mbar_wait(&bar_w, 0);
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int s = it % prm.stages;                   // smem stage
+      const uint32_t ph = (it / prm.stages) & 1;
+      const int a = it & 1;                            // TMEM accumulator
+      const uint32_t pa = (it >> 1) & 1;
+      mbar_wait(&bar_tempty[a], pa ^ 1);               // epilogue has drained this accumulator
+      mbar_wait(&bar_full[s], ph);                     // X tile landed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * prm.n);
+        const uint32_t xa = smem_u32(smem_x + (size_t)s * x_bytes);
+        const uint32_t wa = smem_u32(smem_w);
+        for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll
+          for (int k8 = 0; k8 < KB / 8; ++k8) {
+            uint64_t da = make_desc(xa + kb * SUB_BYTES + k8 * 32);
+            uint64_t db = make_desc(wa + kb * prm.n * KB * 4 + k8 * 32);
+            umma_tf32(d_tmem, da, db, idesc, (kb | k8) != 0);
+          }
+        }
+        umma_commit(&bar_empty[s]);                    // smem stage may be refilled once these MMAs retire
+        umma_commit(&bar_tfull[a]);                    // accumulator ready for the epilogue
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&bar_tfull[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = t * TILE_M + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * prm.n);
+      for (int c0 = 0; c0 < prm.n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < prm.m) {
+          float* dst = prm.y + (size_t)row * prm.n + c0;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                   __uint_as_float(r[4 * v + 3]));
+            if (prm.bias) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(prm.bias + c0) + v);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (prm.accumulate) {
+              float4 p = *(reinterpret_cast<const float4*>(dst) + v);
+              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            *(reinterpret_cast<float4*>(dst) + v) = o;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[s]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(prm.tmem_cols));
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major fp32 [rows, cols] tensor, box = 32 floats (128 B) x box_rows, 128-byte swizzle, OOB rows read as zero
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return B2G_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%d box_rows=%d)", (int)r, (long long)rows, cols, box_rows);
+    return B2G_ECUDA;
+  }
+  return B2G_OK;
+}
+}  // namespace
+
+namespace {
+__global__ void k_transpose(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (r0 + i < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)(r0 + i) * cols + c];
+  __syncthreads();
+  int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (c0 + i < cols && r < rows) out[(size_t)(c0 + i) * rows + r] = tile[threadIdx.x][i];
+}
+}  // namespace
+
+/* out[cols, rows] = in[rows, cols]^T (weights only: a few hundred KB) */
+extern "C" int b2g_transpose(const float* in, int rows, int cols, float* out, void* stream_) {
+  B2G_CHECK_ARG(in && out && rows > 0 && cols > 0, "transpose: bad args");
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
+  k_transpose<<<grid, block, 0, (cudaStream_t)stream_>>>(in, rows, cols, out);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+namespace {
+inline int tc_stages(int n, int k) {          // 2 X stages if they fit next to the resident W, else 1, else unsupported (0)
+  for (int st = 2; st >= 1; --st)
+    if ((size_t)n * k * 4 + (size_t)st * TILE_M * k * 4 + 1024 <= 227 * 1024) return st;
+  return 0;
+}
+}  // namespace
+
+extern "C" int b2g_linear_fwd_tc_supported(int64_t m, int n, int k) {
+  if (m < 1 || n < 32 || n > 256 || (n % 32) != 0 || k < 32 || (k % 32) != 0) return 0;   // epilogue works in 32-column chunks
+  return tc_stages(n, k) > 0 ? 1 : 0;
+}
+
+extern "C" int b2g_linear_fwd_tc(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y, int accumulate,
+                                 void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(x && w && y && b2g_linear_fwd_tc_supported(m, n, k), "linear_fwd_tc: unsupported shape m=%lld n=%d k=%d", (long long)m, n, k);
+  B2G_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y) && (!bias || aligned16(bias)), "linear_fwd_tc: pointers must be 16-byte aligned");
+  CUtensorMap map_x, map_w;
+  int rc = make_map(&map_x, x, m, k, TILE_M);
+  if (rc) return rc;
+  rc = make_map(&map_w, w, n, k, n);
+  if (rc) return rc;
+  TcParams prm;
+  prm.bias = bias; prm.y = y; prm.m = m; prm.n = n; prm.k = k; prm.accumulate = accumulate;
+  int cols = 32;
+  while (cols < 2 * n) cols <<= 1;
+  prm.tmem_cols = cols;
+  prm.stages = tc_stages(n, k);
+  const size_t smem = (size_t)n * k * 4 + (size_t)prm.stages * TILE_M * k * 4 + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    B2G_CUDA(cudaFuncSetAttribute(k_linear_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int64_t tiles = ceil_div(m, TILE_M);
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  k_linear_tf32<<<grid, TC_THREADS, smem, st>>>(map_x, map_w, prm);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}

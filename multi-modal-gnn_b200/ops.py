@@ -7,6 +7,7 @@ CPU tensor raises.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -16,6 +17,22 @@ from . import _lib
 from .graph import CSR, PairIndex, Relation, workspace, _stream
 
 ACT_CODES = {"none": 0, "relu": 1, "leaky_relu": 2, "elu": 3}
+
+# Dense-layer arithmetic: "tf32" = large-M linears on the tcgen05 tensor cores (fp32 operands read as TF32, fp32
+# accumulation in TMEM; ~1e-3 relative, north_star tolerance 1e-2), "fp32" = exact-fp32 SIMT kernels (parity mode).
+PRECISION = os.environ.get("B2G_PRECISION", "tf32")
+TC_MIN_ROWS = 512
+
+
+def set_precision(mode: str):
+    global PRECISION
+    if mode not in ("tf32", "fp32"):
+        raise ValueError(f"precision must be 'tf32' or 'fp32', got {mode!r}")
+    PRECISION = mode
+
+
+def _use_tc(lib, m, n, k) -> bool:
+    return PRECISION == "tf32" and m >= TC_MIN_ROWS and bool(lib.b2g_linear_fwd_tc_supported(m, n, k))
 
 
 def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -65,7 +82,11 @@ def linear_fwd_(x, w, b, y, accumulate=False):
     m, k = x.shape
     n = w.shape[0]
     cost(4 * (m * k + n * k + m * n * (2 if accumulate else 1)), 2 * m * n * k)
-    _run("b2g_linear_fwd", lib.b2g_linear_fwd, x.data_ptr(), w.data_ptr(), _ptr(b), m, n, k, y.data_ptr(), int(accumulate), _stream())
+    if _use_tc(lib, m, n, k) and (b is None or b.data_ptr() % 16 == 0):
+        _run("b2g_linear_fwd_tc", lib.b2g_linear_fwd_tc, x.data_ptr(), w.data_ptr(), _ptr(b), m, n, k, y.data_ptr(), int(accumulate),
+             _stream())
+    else:
+        _run("b2g_linear_fwd", lib.b2g_linear_fwd, x.data_ptr(), w.data_ptr(), _ptr(b), m, n, k, y.data_ptr(), int(accumulate), _stream())
     return y
 
 
@@ -73,6 +94,13 @@ def linear_bwd_input_(dy, w, dx, accumulate=False):
     lib = _lib.load()
     m, n = dy.shape
     k = w.shape[1]
+    if _use_tc(lib, m, k, n):        # dx = dy W  ==  linear(dy, W^T): same tcgen05 kernel on the transposed weight
+        wt = torch.empty((k, n), dtype=torch.float32, device=w.device)
+        _run("b2g_transpose", lib.b2g_transpose, w.data_ptr(), n, k, wt.data_ptr(), _stream())
+        cost(4 * (m * n + n * k + m * k * (2 if accumulate else 1)), 2 * m * n * k)
+        _run("b2g_linear_bwd_input_tc", lib.b2g_linear_fwd_tc, dy.data_ptr(), wt.data_ptr(), None, m, k, n, dx.data_ptr(), int(accumulate),
+             _stream())
+        return dx
     cost(4 * (m * n + n * k + m * k * (2 if accumulate else 1)), 2 * m * n * k)
     _run("b2g_linear_bwd_input", lib.b2g_linear_bwd_input, dy.data_ptr(), w.data_ptr(), m, n, k, dx.data_ptr(), int(accumulate), _stream())
     return dx
