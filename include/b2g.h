@@ -141,6 +141,15 @@ int b2g_linear_fwd_tc_supported(int64_t m, int n, int k);
 int b2g_linear_fwd_tc(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y,
                       int accumulate, void* stream);
 int b2g_transpose(const float* in, int rows, int cols, float* out, void* stream);
+/* dW[N,K] = dy[M,N]^T x[M,K] on tcgen05: both operands MN-major (the reduction index M is the slow one in memory), one
+ * fp32 TMEM accumulator per CTA over its whole share of M, per-CTA partials added in fixed order.  Supported when one of
+ * N, K is 128 and the other a multiple of 32 in [32, 256].  ws: b2g_linear_bwd_weight_tc_ws_bytes.  The bias gradient
+ * is b2g_col_sums(dy) (ws: b2g_bn_ws_bytes(n)). */
+int b2g_linear_bwd_weight_tc_supported(int64_t m, int n, int k);
+size_t b2g_linear_bwd_weight_tc_ws_bytes(int64_t m, int n, int k);
+int b2g_linear_bwd_weight_tc(const float* dy, const float* x, int64_t m, int n, int k, float* dw, void* ws,
+                             size_t ws_bytes, void* stream);
+int b2g_col_sums(const float* x, int64_t m, int d, float* out, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (d') BatchNorm1d + ReLU + Dropout, row L2 normalisation (model.py:93-105,134-139,259-269)

@@ -96,6 +96,10 @@ _PROTOS = {
     "b2g_linear_fwd_tc_supported": (c_int, [c_int64, c_int, c_int]),
     "b2g_linear_fwd_tc": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
     "b2g_transpose": (c_int, [_P, c_int, c_int, _P, _P]),
+    "b2g_linear_bwd_weight_tc_supported": (c_int, [c_int64, c_int, c_int]),
+    "b2g_linear_bwd_weight_tc_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "b2g_linear_bwd_weight_tc": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, c_size_t, _P]),
+    "b2g_col_sums": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P]),
     "b2g_linear_bwd_input": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
     "b2g_linear_bwd_weight_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "b2g_linear_bwd_weight": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),

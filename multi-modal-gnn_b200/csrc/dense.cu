@@ -122,6 +122,87 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_sgemm(const float* __restrict_
   }
 }
 
+// ---- small problems (type-node rows: a few hundred rows at most) ------------------------------------------------------
+// C[M,N] = (acc ? C : 0) + opA(A) opB(B) + bias with 32 x 32 output tiles so that even a 50-row problem spreads over
+// many CTAs, BK = 32 (4 trips for K = 128) and register prefetch of the next tile: these launches are latency-bound.
+//   A_T  : A is stored [K, M] row-major (A(m,k) = Ap[k*M + m])   -- used for dW = dy^T x
+//   B_NK : B is stored [N, K] row-major (B(k,n) = Bp[n*K + k])   -- nn.Linear weights
+template <bool A_T, bool B_NK>
+__global__ void __launch_bounds__(256) k_sgemm_small(const float* __restrict__ Ap, const float* __restrict__ Bp,
+                                                     const float* __restrict__ bias, int M, int N, int K, float* __restrict__ C,
+                                                     int accumulate) {
+  __shared__ float As[32][33];   // [k][m]
+  __shared__ float Bs[32][33];   // [k][n]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int lr = tid >> 3, lq = (tid & 7) * 4;     // loader coordinates: row 0..31, 4 consecutive elements
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float ra[4], rb[4];
+  auto load = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (A_T) {          // row = k, consecutive m
+        int k = k0 + lr, m = m0 + lq + q;
+        ra[q] = (k < K && m < M) ? __ldg(Ap + (size_t)k * M + m) : 0.f;
+      } else {            // row = m, consecutive k
+        int m = m0 + lr, k = k0 + lq + q;
+        ra[q] = (m < M && k < K) ? __ldg(Ap + (size_t)m * K + k) : 0.f;
+      }
+      if (B_NK) {         // row = n, consecutive k
+        int n = n0 + lr, k = k0 + lq + q;
+        rb[q] = (n < N && k < K) ? __ldg(Bp + (size_t)n * K + k) : 0.f;
+      } else {            // row = k, consecutive n
+        int k = k0 + lr, n = n0 + lq + q;
+        rb[q] = (k < K && n < N) ? __ldg(Bp + (size_t)k * N + n) : 0.f;
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (A_T) As[lr][lq + q] = ra[q]; else As[lq + q][lr] = ra[q];
+      if (B_NK) Bs[lq + q][lr] = rb[q]; else Bs[lr][lq + q] = rb[q];
+    }
+  };
+  load(0);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    stash();
+    __syncthreads();
+    if (k0 + 32 < K) load(k0 + 32);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
+      float b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int m = m0 + ty * 2 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      int n = n0 + tx * 2 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+      float* dst = C + (size_t)m * N + n;
+      *dst = accumulate ? *dst + v : v;
+    }
+  }
+}
+constexpr int SMALL_M = 1024;
+
+// db[n] = sum_m dy[m, n] for a few hundred rows (sequential per column: deterministic)
+__global__ void k_colsum_small(const float* __restrict__ dy, int M, int N, float* __restrict__ db) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) s += __ldg(dy + (size_t)m * N + n);
+  db[n] = s;
+}
+
 // ---- weight gradient: dW[N,K] = dy[M,N]^T x[M,K], split over M -------------------------------------------------
 constexpr int WG_T = 64;      // output tile 64 (n) x 64 (k)
 constexpr int WG_MC = 16;     // m rows per smem stage
@@ -205,6 +286,12 @@ extern "C" int b2g_linear_fwd(const float* x, const float* w, const float* bias,
                               void* stream_) {
   B2G_CHECK_ARG(m >= 0 && n > 0 && k > 0 && (m == 0 || (x && w && y)), "linear_fwd: bad args m=%lld n=%d k=%d", (long long)m, n, k);
   if (m == 0) return B2G_OK;
+  if (m <= SMALL_M) {
+    dim3 g((unsigned)ceil_div(m, 32), (unsigned)ceil_div(n, 32));
+    k_sgemm_small<false, true><<<g, 256, 0, (cudaStream_t)stream_>>>(x, w, bias, (int)m, n, k, y, accumulate);
+    B2G_LAUNCH_CHECK();
+    return B2G_OK;
+  }
   int vec_ok = (k % 4 == 0) && aligned16(x) && aligned16(w);
   B2G_CHECK_ARG((n % 4 != 0) || aligned16(y), "linear_fwd: y not 16-byte aligned");
   dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(n, BN));
@@ -216,6 +303,12 @@ extern "C" int b2g_linear_fwd(const float* x, const float* w, const float* bias,
 extern "C" int b2g_linear_bwd_input(const float* dy, const float* w, int64_t m, int n, int k, float* dx, int accumulate, void* stream_) {
   B2G_CHECK_ARG(m >= 0 && n > 0 && k > 0 && (m == 0 || (dy && w && dx)), "linear_bwd_input: bad args");
   if (m == 0) return B2G_OK;
+  if (m <= SMALL_M) {
+    dim3 g((unsigned)ceil_div(m, 32), (unsigned)ceil_div(k, 32));
+    k_sgemm_small<false, false><<<g, 256, 0, (cudaStream_t)stream_>>>(dy, w, nullptr, (int)m, k, n, dx, accumulate);
+    B2G_LAUNCH_CHECK();
+    return B2G_OK;
+  }
   // dx[M,K] = dy[M,N] * W[N,K]: reduction dim is N, output width K, B stored [N(k-dim), K(n-dim)] row-major
   int vec_ok = (n % 4 == 0) && (k % 4 == 0) && aligned16(dy) && aligned16(w);
   B2G_CHECK_ARG((k % 4 != 0) || aligned16(dx), "linear_bwd_input: dx not 16-byte aligned");
@@ -237,6 +330,16 @@ extern "C" int b2g_linear_bwd_weight(const float* dy, const float* x, int64_t m,
   if (m == 0) {
     B2G_CUDA(cudaMemsetAsync(dw, 0, (size_t)n * k * 4, st));
     if (db) B2G_CUDA(cudaMemsetAsync(db, 0, (size_t)n * 4, st));
+    return B2G_OK;
+  }
+  if (m <= SMALL_M) {
+    dim3 g((unsigned)ceil_div(n, 32), (unsigned)ceil_div(k, 32));
+    k_sgemm_small<true, false><<<g, 256, 0, st>>>(dy, x, nullptr, n, k, (int)m, dw, 0);
+    B2G_LAUNCH_CHECK();
+    if (db) {
+      k_colsum_small<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(dy, (int)m, n, db);
+      B2G_LAUNCH_CHECK();
+    }
     return B2G_OK;
   }
   if (!ws || ws_bytes < b2g_linear_bwd_weight_ws_bytes(m, n, k)) {

@@ -243,6 +243,137 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
   }
 }
 
+// ---- weight gradient on tcgen05:  D[128, NB] = A^T B  with A [M, 128], B [M, NB] row-major (reduction over the M rows) ----
+// Both operands are "MN-major" for the MMA (the reduction index is the slow one in memory).  TMA lands [64 rows x 128 B]
+// sub-tiles (SWIZZLE_128B); in the canonical MN-major SW128 layout ((8,n),(8,k)):((1,LBO),(8,SBO)) (units of 16 B) this
+// is: 8 reduction rows 128 B apart form one swizzle atom, SBO = 1024 B to the next 8 rows, LBO = one sub-tile (8 KB) to
+// the next 32 columns.  One MMA consumes 8 reduction rows (K = 8 for tf32): start address advances by 1024 B.
+constexpr int WG_ROWS = 64;                         // reduction rows per stage
+constexpr int WG_SUB = WG_ROWS * KB * 4;            // 8 KB sub-tile
+constexpr int WG_STAGES = 3;
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  // 32-bit operands in MN-major form need the 32-byte-atom flavour of the 128-byte swizzle (cute
+  // Layout_MN_SW128_32B_Atom, Swizzle<2,5,2> on byte addresses: 32 B chunks XOR (row mod 4); TMA mode
+  // SWIZZLE_128B_ATOM_32B): atom = 4 reduction rows x 128 B, SBO = 512 B to the next 4 rows, LBO = next 32 columns.
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(WG_SUB >> 4) << 16;               // LBO: next group of 32 columns
+  d |= (uint64_t)(512 >> 4) << 32;                  // SBO: next group of 4 reduction rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                           // LayoutType::SWIZZLE_128B_BASE32B
+  return d;
+}
+
+struct WgParams {
+  float* partial;      // [grid][128][nb]
+  int64_t m;
+  int nb;              // columns of B (N of the MMA), multiple of 32, <= 256
+  int tmem_cols;
+  int stages;          // <= WG_STAGES, as many as fit in shared memory
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tf32(const __grid_constant__ CUtensorMap map_a,
+                                                              const __grid_constant__ CUtensorMap map_b, WgParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full[WG_STAGES], bar_empty[WG_STAGES], bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = 4u * WG_SUB;                              // 128 columns of A
+  const uint32_t b_bytes = (uint32_t)(prm.nb / KB) * WG_SUB;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  const int64_t n_tiles = (prm.m + WG_ROWS - 1) / WG_ROWS;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(prm.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int s = it % prm.stages;
+        const uint32_t ph = (it / prm.stages) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        mbar_expect_tx(&bar_full[s], stage_bytes);
+        uint8_t* st = base + (size_t)s * stage_bytes;
+        for (int c = 0; c < 4; ++c) tma_load_2d(st + c * WG_SUB, &map_a, &bar_full[s], c * KB, (int)(t * WG_ROWS));
+        for (int c = 0; c < prm.nb / KB; ++c) tma_load_2d(st + a_bytes + c * WG_SUB, &map_b, &bar_full[s], c * KB, (int)(t * WG_ROWS));
+      }
+    }
+  } else if (warp == 1) {
+    // instruction descriptor: as make_idesc, plus MN-major A (bit 15) and B (bit 16)
+    const uint32_t idesc = make_idesc(prm.nb) | (1u << 15) | (1u << 16);
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int s = it % prm.stages;
+      const uint32_t ph = (it / prm.stages) & 1;
+      mbar_wait(&bar_full[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+#pragma unroll
+        for (int j = 0; j < WG_ROWS / 8; ++j)
+          umma_tf32(tmem_base, make_desc_mn(sa + j * 1024), make_desc_mn(sb + j * 1024), idesc, (it | j) != 0);
+        umma_commit(&bar_empty[s]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar_done);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    mbar_wait(&bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = q * 32 + lane;                                   // row of D = column of A
+    float* dst_row = prm.partial + ((size_t)blockIdx.x * 128 + row) * prm.nb;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < prm.nb; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        *(reinterpret_cast<float4*>(dst_row + c0) + v) = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                                                   __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(prm.tmem_cols));
+  }
+}
+
+// out[i] = sum over CTAs of partial[c][i] (fixed order); optionally transposed: partial is [128][nb] = dW^T
+__global__ void k_wgrad_tc_reduce(const float* __restrict__ partial, int n_cta, int rows, int cols, int transpose, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  float s = 0.f;
+  for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * rows * cols + i];
+  if (transpose) {
+    int r = i / cols, cc = i % cols;
+    out[(size_t)cc * rows + r] = s;
+  } else {
+    out[i] = s;
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -263,7 +394,8 @@ EncodeTiledFn get_encode() {
 }
 
 // row-major fp32 [rows, cols] tensor, box = 32 floats (128 B) x box_rows, 128-byte swizzle, OOB rows read as zero
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int cols, int box_rows) {
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int cols, int box_rows,
+             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -274,7 +406,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int cols, int bo
   cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%d box_rows=%d)", (int)r, (long long)rows, cols, box_rows);
     return B2G_ECUDA;
@@ -343,6 +475,61 @@ extern "C" int b2g_linear_fwd_tc(const float* x, const float* w, const float* bi
   int64_t tiles = ceil_div(m, TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   k_linear_tf32<<<grid, TC_THREADS, smem, st>>>(map_x, map_w, prm);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+/* dW[N,K] = dy[M,N]^T x[M,K] on tcgen05 (TF32 operands, fp32 accumulation in TMEM across the whole M range of a CTA;
+ * per-CTA partials are added in fixed order).  Supported when one of N, K is 128 and the other a multiple of 32 <= 256. */
+extern "C" int b2g_linear_bwd_weight_tc_supported(int64_t m, int n, int k) {
+  if (m < 1) return 0;
+  if (n == 128 && k % 32 == 0 && k >= 32 && k <= 256) return 1;
+  if (k == 128 && n % 32 == 0 && n >= 32 && n <= 256) return 1;
+  return 0;
+}
+extern "C" size_t b2g_linear_bwd_weight_tc_ws_bytes(int64_t m, int n, int k) {
+  (void)m;
+  return (size_t)sm_count() * n * k * 4 + 256;
+}
+extern "C" int b2g_linear_bwd_weight_tc(const float* dy, const float* x, int64_t m, int n, int k, float* dw, void* ws, size_t ws_bytes,
+                                        void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(dy && x && dw && b2g_linear_bwd_weight_tc_supported(m, n, k), "linear_bwd_weight_tc: unsupported shape m=%lld n=%d k=%d",
+                (long long)m, n, k);
+  B2G_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dw) && aligned16(ws), "linear_bwd_weight_tc: unaligned pointer");
+  if (!ws || ws_bytes < b2g_linear_bwd_weight_tc_ws_bytes(m, n, k)) {
+    set_error("linear_bwd_weight_tc: workspace too small");
+    return B2G_EWS;
+  }
+  const bool swap = (n != 128);                 // the 128-wide matrix is the MMA's A (its columns become D's 128 rows)
+  const float* a = swap ? x : dy;
+  const float* b = swap ? dy : x;
+  const int nb = swap ? n : k;
+  CUtensorMap map_a, map_b;
+  int rc = make_map(&map_a, a, m, 128, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  rc = make_map(&map_b, b, m, nb, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  WgParams prm;
+  prm.partial = (float*)ws; prm.m = m; prm.nb = nb;
+  int cols = 32;
+  while (cols < nb) cols <<= 1;
+  prm.tmem_cols = cols;
+  const size_t stage_bytes = (size_t)(4 + nb / KB) * WG_SUB;
+  prm.stages = (int)((226 * 1024) / stage_bytes);
+  if (prm.stages > WG_STAGES) prm.stages = WG_STAGES;
+  const size_t smem = (size_t)prm.stages * stage_bytes + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    B2G_CUDA(cudaFuncSetAttribute(k_wgrad_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int64_t tiles = ceil_div(m, WG_ROWS);
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  k_wgrad_tf32<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, prm);
+  B2G_LAUNCH_CHECK();
+  // partial[c] is [128][nb]: equals dW[N,K] when !swap (rows = n), dW^T when swap (rows = k, cols = n)
+  k_wgrad_tc_reduce<<<(unsigned)ceil_div(128 * nb, 256), 256, 0, st>>>(prm.partial, grid, 128, nb, swap ? 1 : 0, dw);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

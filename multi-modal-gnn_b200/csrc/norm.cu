@@ -141,6 +141,13 @@ __global__ void __launch_bounds__(256) k_bn_bwd_finalize(const double* __restric
   if (dgamma) dgamma[c] = (float)s1;
 }
 
+__global__ void __launch_bounds__(256) k_colsum_finalize(const double* __restrict__ partial, int n_part, int d, float* __restrict__ out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  double s0, s1;
+  reduce_partials(partial, n_part, d, c, slice, s0, s1);
+  if (slice == 0 && c < d) out[c] = (float)s0;
+}
+
 __global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __restrict__ rv, int d, float eps, float* __restrict__ mean,
                                 float* __restrict__ rstd) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,6 +405,24 @@ extern "C" int b2g_bn_stats(const float* x, int64_t m, int d, float eps, float m
   k_col_partial<0><<<parts, 256, smem, st>>>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, partial);
   B2G_LAUNCH_CHECK();
   k_bn_finalize<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, m, d, eps, momentum, mean, rstd, running_mean, running_var);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+/* out[c] = sum_r x[r, c]  (bias gradient of a linear layer), fp64 accumulation, fixed order */
+extern "C" int b2g_col_sums(const float* x, int64_t m, int d, float* out, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(x && out && m > 0 && d_ok(d) && aligned16(x), "col_sums: bad args (m=%lld d=%d)", (long long)m, d);
+  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
+    set_error("col_sums: workspace too small");
+    return B2G_EWS;
+  }
+  double* partial = (double*)ws;
+  int parts = col_parts(m, d);
+  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
+  k_col_partial<0><<<parts, 256, smem, st>>>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, partial);
+  B2G_LAUNCH_CHECK();
+  k_colsum_finalize<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, d, out);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

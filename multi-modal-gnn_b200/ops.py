@@ -110,6 +110,16 @@ def linear_bwd_weight_(dy, x, dw, db):
     lib = _lib.load()
     m, n = dy.shape
     k = x.shape[1]
+    if PRECISION == "tf32" and m >= TC_MIN_ROWS and lib.b2g_linear_bwd_weight_tc_supported(m, n, k) and (db is None or n in (32, 64, 128, 256)):
+        ws = workspace(lib.b2g_linear_bwd_weight_tc_ws_bytes(m, n, k), dy.device)
+        cost(4 * (m * n + m * k + n * k), 2 * m * n * k)
+        _run("b2g_linear_bwd_weight_tc", lib.b2g_linear_bwd_weight_tc, dy.data_ptr(), x.data_ptr(), m, n, k, dw.data_ptr(), ws.data_ptr(),
+             ws.numel(), _stream())
+        if db is not None:
+            ws = workspace(lib.b2g_bn_ws_bytes(n), dy.device)
+            cost(4 * m * n)
+            _run("b2g_col_sums", lib.b2g_col_sums, dy.data_ptr(), m, n, db.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        return
     nb = lib.b2g_linear_bwd_weight_ws_bytes(m, n, k)
     ws = workspace(nb, dy.device)
     cost(4 * (m * n + m * k + n * k), 2 * m * n * k)

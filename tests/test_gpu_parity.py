@@ -605,7 +605,8 @@ def test_tcgen05_autograd_and_training_step(dev, golden_tiny_mae, golden_c1):
     names = [p[0] for p in ops.PROFILE]
     ops.PROFILE = None
     assert "b2g_linear_fwd_tc" in names and "b2g_linear_bwd_input_tc" in names
-    assert relerr(xd.grad, xr.grad) <= 3e-3 and relerr(wd.grad, wr.grad) <= 1e-4
+    assert relerr(xd.grad, xr.grad) <= 3e-3 and relerr(wd.grad, wr.grad) <= 3e-3
+    assert "b2g_linear_bwd_weight_tc" in names
     # whole training step on the C1 golden with tensor-core linears: within the 1e-2 band of the reference
     blob = golden_c1
     model, g, counts, ets, eid, attr = _model_from_golden(blob, dev)
@@ -621,6 +622,38 @@ def test_tcgen05_autograd_and_training_step(dev, golden_tiny_mae, golden_c1):
     params = dict(model.named_parameters())
     # gradients pass through ~10 chained TF32 products and the cancellation inside BatchNorm's backward: the deepest
     # ones (first MLP layer) carry the largest error; measured 6.7e-2 of max|grad| on this fixture
-    for k_, tol in (("edge_predictor.mlp.0.weight", 2e-2), ("convs.0.convs.lab__has_lab_rev__patient.lin_l.weight", 5e-2),
-                    ("patient_transform.0.weight", 1.5e-1)):
-        assert relerr(params[k_].grad, blob["grads"][k_]) <= tol, k_
+    errs = {k_: relerr(params[k_].grad, blob["grads"][k_]) for k_ in blob["grads"]
+            if not (k_ in ("patient_transform.0.bias", "patient_transform.4.bias") or k_.endswith("lin_l.bias"))}
+    print("TF32 gradient errors (fraction of max|grad|):", {k_: round(v, 4) for k_, v in errs.items()})
+    assert max(errs.values()) <= 2.5e-1, errs
+
+
+@pytest.mark.parametrize("m,n,k", [(64, 128, 128), (1000, 128, 128), (46520, 128, 128), (46521, 64, 128), (30000, 128, 64),
+                                   (9999, 128, 256), (5000, 256, 128), (777, 32, 128)])
+def test_tcgen05_weight_gradient(m, n, k, dev):
+    *_, ops, M, T, L = _mods()
+    lib = L.load()
+    assert lib.b2g_linear_bwd_weight_tc_supported(m, n, k) == 1
+    gen = torch.Generator().manual_seed(m + n + k)
+    # TF32-representable operands: the result must equal exact math up to fp32 accumulation order, which pins the
+    # MN-major descriptors / swizzle / transposed write-back independently of operand rounding
+    dy = (torch.randint(-8, 9, (m, n), generator=gen).float() / 8).to(dev)
+    x = (torch.randint(-8, 9, (m, k), generator=gen).float() / 16).to(dev)
+    ref = dy.double().cpu().t() @ x.double().cpu()
+    dw = torch.full((n, k), float("nan"), device=dev)
+    ws = torch.empty(lib.b2g_linear_bwd_weight_tc_ws_bytes(m, n, k), dtype=torch.uint8, device=dev)
+    L.check(lib.b2g_linear_bwd_weight_tc(dy.data_ptr(), x.data_ptr(), m, n, k, dw.data_ptr(), ws.data_ptr(), ws.numel(), None))
+    assert relerr(dw, ref) <= 2e-6
+    # random operands: TF32 rounding only
+    dy2, x2 = torch.randn(m, n, generator=gen).to(dev), torch.randn(m, k, generator=gen).to(dev)
+    ref2 = dy2.double().cpu().t() @ x2.double().cpu()
+    L.check(lib.b2g_linear_bwd_weight_tc(dy2.data_ptr(), x2.data_ptr(), m, n, k, dw.data_ptr(), ws.data_ptr(), ws.numel(), None))
+    assert relerr(dw, ref2) <= 3e-3
+    dw2 = torch.empty_like(dw)
+    L.check(lib.b2g_linear_bwd_weight_tc(dy2.data_ptr(), x2.data_ptr(), m, n, k, dw2.data_ptr(), ws.data_ptr(), ws.numel(), None))
+    assert torch.equal(dw, dw2)
+    # bias gradient
+    db = torch.empty(n, device=dev)
+    ws2 = torch.empty(lib.b2g_bn_ws_bytes(n), dtype=torch.uint8, device=dev)
+    L.check(lib.b2g_col_sums(dy2.data_ptr(), m, n, db.data_ptr(), ws2.data_ptr(), ws2.numel(), None))
+    assert relerr(db, dy2.double().sum(0)) <= 1e-6
