@@ -207,24 +207,23 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def allreduce_grads():
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
-            dist.all_reduce(flat)
-            flat /= world
-            off = 0
-            for p in model.parameters():
-                if p.grad is not None:
-                    n = p.grad.numel()
-                    p.grad.copy_(flat[off:off + n].view_as(p.grad)); off += n
+        """the only NCCL traffic of the step: one flat all-reduce of the gradient bucket (north_star)"""
+        grads = [p.grad for p in model.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat /= world
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g)); off += n
+
+    if world > 1:
+        trainer.grad_hook = allreduce_grads
+    if not args.no_graph:
+        trainer.enable_cuda_graph()
 
     def step_device(i):
-        trainer.optimizer.zero_grad()
-        pred = model.predict_lab_values(trainer.data, pi, li)
-        loss = ops.weighted_loss(pred, ev, li, trainer.lab_weights, sup_dev[i], "mse")
-        loss.backward()
-        allreduce_grads()
-        trainer.optimizer.step()
-        return loss
+        return trainer.train_step(pi, li, ev, sup_dev[i])
 
     model.train()
     clocks = ClockSampler(local_rank)
@@ -251,7 +250,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = int(lib.b2g_launch_count())
+    launches = int(lib.b2g_launch_count())            # eager launches in the timed region ...
+    if not args.no_graph:
+        launches += trainer.graph_kernel_nodes * args.steps   # ... plus the libb2g kernel nodes of every graph replay
     step_ms = [s.elapsed_time(e) for s, e in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -260,16 +261,17 @@ def run_ours(args):
     final_loss = float(loss.item())
 
     # ---- timed: end to end through the public Trainer API with host inputs ----
-    pi_h, li_h, ev_h = pi.cpu().pin_memory(), li.cpu().pin_memory(), ev.cpu().pin_memory()
-    pi_d, li_d, ev_d = torch.empty_like(pi), torch.empty_like(li), torch.empty_like(ev)
+    # Per-step host input of Trainer.train_epoch is the supervision mask the host-side EdgeMasker draws for that epoch
+    # (train.py:150-159); the split's pair indices / targets are dataset state uploaded once with the graph
+    # (Trainer.__init__: data.to(device)), exactly like the reference.  Each step: pinned host mask -> device, one
+    # train_step, loss read back to the host.
     sup_d = torch.empty(n_train, dtype=torch.bool, device=dev)
-    h2d = pi_h.numel() * 8 + li_h.numel() * 8 + ev_h.numel() * 4 + n_train
+    h2d = n_train
     e2e_steps = max(3, args.steps)
 
     def step_e2e(i):
-        pi_d.copy_(pi_h, non_blocking=True); li_d.copy_(li_h, non_blocking=True)
-        ev_d.copy_(ev_h, non_blocking=True); sup_d.copy_(sup_host[i % total_steps], non_blocking=True)
-        loss = trainer.train_step(pi_d, li_d, ev_d, sup_d)
+        sup_d.copy_(sup_host[i % total_steps], non_blocking=True)
+        loss = trainer.train_step(pi, li, ev, sup_d)
         return float(loss.item())                  # device -> host read of the step's result
 
     step_e2e(0)
@@ -289,6 +291,8 @@ def run_ours(args):
     # ---- one instrumented step: per-kernel CUDA-event durations -> dominant kernel + roofline ----
     roof, kernels = None, None
     if rank == 0:
+        trainer.enable_cuda_graph(False)         # per-call events cannot live inside a captured graph
+        step_device(args.warmup)
         ops.PROFILE = []
         flush.fill_(1)
         step_device(args.warmup)
@@ -320,7 +324,7 @@ def run_ours(args):
                 "config": {"workload": f"{args.workload}: {spec.n_patient} patients/{spec.n_lab} labs/{spec.n_dx} dx/{spec.n_med} meds, "
                                        f"{spec.e_lab}/{spec.e_dx}/{spec.e_med} edges per GPU, d=128, L=2, dropout 0.2, mse + lab weights, "
                                        f"{n_train} train pairs, 20% supervised, Adam",
-                           "step": "Trainer.train_epoch body: predict_lab_values fwd + weighted loss + bwd + Adam",
+                           "step": "Trainer.train_step: predict_lab_values fwd + weighted loss + bwd" + (" (one CUDA graph replay)" if not args.no_graph else "") + " + Adam",
                            "l2": "flushed with a 256 MiB write before every timed step; per-step working set (>1 GB) also exceeds the 126 MB L2",
                            "parallelism": f"patient-partitioned x{world}" if world > 1 else "single GPU"},
                 "e2e": {"value": edges_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
@@ -347,6 +351,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step launch by launch instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -102,6 +102,18 @@ int b2g_gather_reduce_chunked(const b2g_rel_t* h_rel, const int32_t* item_row, c
                               const int32_t* row_item_ptr, int64_t n_items, int32_t chunk, int64_t n_rows,
                               int d, float* out, int accumulate, void* ws, size_t ws_bytes, void* stream);
 
+/* Tensor-core formulation of the same contraction for the dense-ish bipartite EHR relations (millions of patients x a
+ * vocabulary of <= 256 labs / diagnoses / drugs): the adjacency is held as a dense fp32 [n_big, pad] matrix D
+ * (b2g_dense_adjacency; entries 0/1, or 0 / (1/deg_row)) and the four products of a relation become tcgen05 GEMMs:
+ *   mean onto the small side   agg_T = diag(1/deg_T) D^T x_P      -> b2g_linear_bwd_weight_tc(dy = D, x = x_P) + b2g_row_scale
+ *   its backward               dx_P  = D (dagg_T / deg_T)         -> b2g_linear_fwd_tc(x = D, w = b2g_transpose_pad(dagg_T, 1/deg_T))
+ *   mean onto the big side     out_P += D' Y_T, D' = diag(1/deg_P) D -> b2g_linear_fwd_tc(x = D', w = b2g_transpose_pad(Y_T), accumulate)
+ *   its backward               dY_T  = D'^T dout_P                -> b2g_linear_bwd_weight_tc(dy = D', x = dout_P) */
+int b2g_dense_adjacency(const int32_t* rowptr, const int32_t* col, const float* row_val, int64_t n_rows, int pad,
+                        float* out, void* stream);
+int b2g_transpose_pad(const float* in, const float* scale, int rows, int cols, int pad, float* out, void* stream);
+int b2g_row_scale(const float* in, const float* scale, int64_t rows, int d, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (c) embedding tables -- nn.Embedding(arange(N)) fwd / dense grad (model.py:225-226)
  * ---------------------------------------------------------------------------------------------- */

@@ -88,6 +88,9 @@ _PROTOS = {
     "b2g_gather_reduce": (c_int, [ctypes.POINTER(RelT), c_int, c_int64, c_int, _P, c_int, _P]),
     "b2g_gather_reduce_chunked": (c_int, [ctypes.POINTER(RelT), _P, _P, _P, c_int64, c_int32, c_int64, c_int, _P, c_int,
                                           _P, c_size_t, _P]),
+    "b2g_dense_adjacency": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
+    "b2g_transpose_pad": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "b2g_row_scale": (c_int, [_P, _P, c_int64, c_int, _P, _P]),
     "b2g_gather_rows": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
     "b2g_gather_add_rows": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P]),
     "b2g_scatter_values": (c_int, [_P, _P, c_int64, _P, _P]),

@@ -90,6 +90,16 @@ struct Philox {
   }
 };
 
+// CUDA-graph friendly seeding: when bit 63 of the stream id is set, `seed` is a DEVICE POINTER to the 64-bit seed, so
+// a captured graph can be replayed with a fresh seed written by the host before each replay.
+constexpr uint64_t SEED_IS_POINTER = 1ull << 63;
+__device__ __forceinline__ void resolve_seed(uint64_t& seed, uint64_t& sid) {
+  if (sid & SEED_IS_POINTER) {
+    seed = *reinterpret_cast<const uint64_t*>(seed);
+    sid &= ~SEED_IS_POINTER;
+  }
+}
+
 // keep-scale for 4 consecutive elements starting at element index 4*quad of dropout stream `sid`
 __device__ __forceinline__ float4 dropout_scale4(uint64_t seed, uint64_t sid, uint64_t quad, float p) {
   Philox ph(seed);

@@ -65,6 +65,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) k_decoder_fwd(const float* __r
     sw3[threadIdx.x] = w3[threadIdx.x];
   }
   __syncthreads();
+  if (p_drop > 0.f) {
+    resolve_seed(seed, sid1);
+    sid2 &= ~SEED_IS_POINTER;
+  }
   const float bias3 = __ldg(b3);
   for (int64_t i = (int64_t)blockIdx.x * DEC_THREADS + threadIdx.x; i < M; i += (int64_t)gridDim.x * DEC_THREADS) {
     float z[H1];
@@ -201,6 +205,10 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decoder_bwd(const float* __rest
     sw3[threadIdx.x] = w3[threadIdx.x];
   }
   __syncthreads();
+  if (p_drop > 0.f) {
+    resolve_seed(seed, sid1);
+    sid2 &= ~SEED_IS_POINTER;
+  }
   const int n_active = *n_active_ptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) k_col_partial(const float* __restrict__ x
                                                      const float* __restrict__ gamma, const float* __restrict__ beta, int relu, float p_drop,
                                                      uint64_t seed, uint64_t sid, double* __restrict__ partial) {
   extern __shared__ double sm[];  // [rows_per_pass][2][d]
+  if (MODE == 1 && p_drop > 0.f) resolve_seed(seed, sid);
   const int tpr = d >> 2;               // threads per row (float4 each)
   const int rpp = 256 / tpr;            // rows per pass of the block
   const int cg = threadIdx.x % tpr, rs = threadIdx.x / tpr;
@@ -159,6 +160,7 @@ __global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __res
 __global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ x, int64_t n4, int d, const float* __restrict__ mean,
                                                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                   int relu, float p_drop, uint64_t seed, uint64_t sid, float* __restrict__ y) {
+  if (p_drop > 0.f) resolve_seed(seed, sid);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)((i * 4) % d);
     float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + i);
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
                                                       const float* __restrict__ gamma, const float* __restrict__ beta, int relu, float p_drop,
                                                       uint64_t seed, uint64_t sid, int batch_stats, const double* __restrict__ sums,
                                                       float* __restrict__ dx) {
+  if (p_drop > 0.f) resolve_seed(seed, sid);
   const float inv_m = 1.0f / (float)m;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)((i * 4) % d);
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
 // ---- ReLU / Dropout --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_relu_dropout_fwd(const float* __restrict__ x, int64_t n, int relu, float p, uint64_t seed, uint64_t sid,
                                                           float* __restrict__ y) {
+  if (p > 0.f) resolve_seed(seed, sid);
   const int64_t n4 = (n + 3) >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(256) k_relu_dropout_fwd(const float* __restric
 // dx = dy * mask * [y > 0]  (y is the forward OUTPUT: y > 0 <=> pre-activation > 0 and kept)
 __global__ void __launch_bounds__(256) k_relu_dropout_bwd(const float* __restrict__ y, const float* __restrict__ dy, int64_t n, int relu, float p,
                                                           uint64_t seed, uint64_t sid, float* __restrict__ dx) {
+  if (p > 0.f) resolve_seed(seed, sid);
   const int64_t n4 = (n + 3) >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(256) k_relu_dropout_bwd(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) k_dropout_mask(int64_t n, float p, uint64_t seed, uint64_t sid, float* __restrict__ mask) {
+  if (p > 0.f) resolve_seed(seed, sid);
   const int64_t n4 = (n + 3) >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);

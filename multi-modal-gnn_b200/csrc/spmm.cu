@@ -153,6 +153,76 @@ __global__ void k_gather_values(const float* __restrict__ src, const int64_t* __
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) out[i] = src[idx[i]];
 }
+
+// ---- dense adjacency for the tensor-core formulation of the aggregation -------------------------------------------------
+// EHR relations are bipartite between millions of patients and a vocabulary of <= 256 labs / diagnoses / drugs, with
+// 5-70 % of all possible pairs present: the adjacency is better held as a dense [n_big, pad] fp32 matrix (entries 0/1 or
+// 0 / (1/deg_row), all exactly representable or uniformly rounded in TF32) and multiplied on the tensor cores.
+__global__ void __launch_bounds__(256) k_dense_adj(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                   const float* __restrict__ row_val, int64_t n_rows, int pad, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  float* o = out + (size_t)row * pad;
+  for (int c = lane; c < pad; c += 32) o[c] = 0.f;
+  __syncwarp();
+  const float v = row_val ? __ldg(row_val + row) : 1.0f;
+  const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+  for (int j = b + lane; j < e; j += 32) atomicAdd(o + __ldg(col + j), v);   // equal addends: order-independent, exact
+}
+
+// out[c, r] = (r < rows ? in[r, c] * scale[r] : 0)   in [rows, cols] -> out [cols, pad]
+__global__ void k_transpose_pad(const float* __restrict__ in, const float* __restrict__ scale, int rows, int cols, int pad,
+                                float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * cols + c] * (scale ? scale[r] : 1.f) : 0.f;
+  }
+  __syncthreads();
+  const int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (c0 + i < cols && r < pad) out[(size_t)(c0 + i) * pad + r] = tile[threadIdx.x][i];
+}
+
+__global__ void k_row_scale(const float* __restrict__ in, const float* __restrict__ scale, int64_t n4, int d4, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(in)[i];
+  float s = __ldg(scale + i / d4);
+  reinterpret_cast<float4*>(out)[i] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+}
+}  // namespace
+
+/* Dense [n_rows, pad] adjacency of a CSR: out[r, col[j]] += (row_val ? row_val[r] : 1) for j in row r, zero elsewhere. */
+extern "C" int b2g_dense_adjacency(const int32_t* rowptr, const int32_t* col, const float* row_val, int64_t n_rows, int pad, float* out,
+                                   void* stream_) {
+  B2G_CHECK_ARG(rowptr && col && out && n_rows > 0 && pad > 0, "dense_adjacency: bad args");
+  k_dense_adj<<<(unsigned)ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream_>>>(rowptr, col, row_val, n_rows, pad, out);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+/* out[cols, pad] = (in[rows, cols] * scale[rows, None])^T, zero-padded to `pad` columns (scale may be NULL). */
+extern "C" int b2g_transpose_pad(const float* in, const float* scale, int rows, int cols, int pad, float* out, void* stream_) {
+  B2G_CHECK_ARG(in && out && rows > 0 && cols > 0 && pad >= rows, "transpose_pad: bad args");
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(pad, 32)), block(32, 8);
+  k_transpose_pad<<<grid, block, 0, (cudaStream_t)stream_>>>(in, scale, rows, cols, pad, out);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+/* out[r, :] = in[r, :] * scale[r]   (d % 4 == 0) */
+extern "C" int b2g_row_scale(const float* in, const float* scale, int64_t rows, int d, float* out, void* stream_) {
+  B2G_CHECK_ARG(in && scale && out && rows > 0 && d > 0 && d % 4 == 0 && aligned16(in) && aligned16(out), "row_scale: bad args");
+  int64_t n4 = rows * d / 4;
+  k_row_scale<<<(unsigned)ceil_div(n4, 256), 256, 0, (cudaStream_t)stream_>>>(in, scale, n4, d / 4, out);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+namespace {
 }  // namespace
 
 extern "C" int b2g_scatter_values(const float* vals, const int64_t* idx, int64_t m, float* out, void* stream_) {

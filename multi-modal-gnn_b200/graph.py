@@ -105,10 +105,51 @@ class Relation:
         self.n_edges = int(edge_index.shape[1])
         self.by_dst = CSR(edge_index[1], edge_index[0], n_dst, n_src)
         self.by_src = CSR(edge_index[0], edge_index[1], n_src, n_dst)
+        self._dense = None
+        self._dense_checked = False
 
     @property
     def inv_deg_dst(self):
         return self.by_dst.inv_deg
+
+    def dense(self, d: int) -> Optional["DenseAdjacency"]:
+        """Dense [n_big, pad] adjacency for the tensor-core formulation (None when the relation does not qualify:
+        small side > 256 nodes, big side too small to matter, sparser than the break-even, or over the memory budget)."""
+        if self._dense_checked:
+            return self._dense
+        self._dense_checked = True
+        lib = _lib.load()
+        small_is_src = self.n_src < self.n_dst
+        n_small, n_big = (self.n_src, self.n_dst) if small_is_src else (self.n_dst, self.n_src)
+        pad = (n_small + 31) // 32 * 32
+        if n_small > 256 or n_big < 4096 or self.n_edges == 0:
+            return None
+        # dense row (pad * 4 B) vs gathered rows (deg * d * 4 B): only worth it when the relation is dense enough
+        if self.n_edges / n_big * d < pad:
+            return None
+        if not (lib.b2g_linear_fwd_tc_supported(n_big, d, pad) and lib.b2g_linear_bwd_weight_tc_supported(n_big, pad, d)):
+            return None
+        nbytes = n_big * pad * 4
+        if DenseAdjacency.bytes_in_use + nbytes > DenseAdjacency.budget_bytes:
+            return None
+        csr = self.by_dst if small_is_src else self.by_src          # rows = the big side
+        mat = torch.empty((n_big, pad), dtype=torch.float32, device=csr.rowptr.device)
+        row_val = csr.inv_deg if small_is_src else None              # mean onto the big side: rows pre-scaled by 1/deg
+        _lib.check(lib.b2g_dense_adjacency(csr.rowptr.data_ptr(), csr.col.data_ptr(), None if row_val is None else row_val.data_ptr(),
+                                           n_big, pad, mat.data_ptr(), _stream()), "b2g_dense_adjacency")
+        DenseAdjacency.bytes_in_use += nbytes
+        self._dense = DenseAdjacency(mat, pad, n_small, n_big, small_is_src)
+        return self._dense
+
+
+class DenseAdjacency:
+    """mat [n_big, pad]: entries 1 (big side is the source: plain adjacency) or 1/deg_big (big side is the destination:
+    row-normalised adjacency); columns >= n_small are zero."""
+    budget_bytes = 8 << 30
+    bytes_in_use = 0
+
+    def __init__(self, mat, pad, n_small, n_big, big_is_dst):
+        self.mat, self.pad, self.n_small, self.n_big, self.big_is_dst = mat, pad, n_small, n_big, big_is_dst
 
 
 class GraphIndex:

@@ -40,16 +40,25 @@ class _DropoutStreams:
     """Per-call dropout bookkeeping: one 64-bit seed drawn from torch's CPU generator (so
     ``torch.manual_seed`` makes runs repeatable) and a running stream id, one per dropout site."""
 
-    def __init__(self, active: bool):
-        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if active else 0
+    SEED_IS_POINTER = 1 << 63          # csrc/common.cuh: `seed` is a device pointer to the 64-bit seed
+
+    def __init__(self, active: bool, seed_buffer: Optional[torch.Tensor] = None):
         self.next_id = 0
         self.log: List[Tuple[str, int]] = []
+        self.flag = 0
+        if active and seed_buffer is not None:
+            # CUDA-graph mode: kernels read the seed from device memory; the owner of the graph rewrites that
+            # buffer before every replay (trainer.py), so nothing here may touch it.
+            self.seed = seed_buffer.data_ptr()
+            self.flag = self.SEED_IS_POINTER
+        else:
+            self.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if active else 0
 
     def take(self, tag: str = "") -> int:
         sid = self.next_id
         self.next_id += 1
         self.log.append((tag, sid))
-        return sid
+        return sid | self.flag
 
 
 def _bn_act_drop(x, bn: Optional[nn.BatchNorm1d], training: bool, act: int, p: float, streams: _DropoutStreams, tag: str):
@@ -174,6 +183,7 @@ class HeteroRGCN(nn.Module):
         self.degree_threshold = 6
         self._pair_plans: "OrderedDict[int, _PairPlan]" = OrderedDict()
         self._last_streams: Optional[_DropoutStreams] = None
+        self._seed_buffer: Optional[torch.Tensor] = None      # set by Trainer.enable_cuda_graph()
         self._register_load_state_dict_pre_hook(self._rename_pyg24_keys)
         logging.info(f"Initialized HeteroRGCN with hidden_dim={hidden_dim}, num_layers={num_layers}")
 
@@ -256,7 +266,7 @@ class HeteroRGCN(nn.Module):
         return x
 
     def _streams(self) -> _DropoutStreams:
-        s = _DropoutStreams(self.training and self.dropout > 0)
+        s = _DropoutStreams(self.training and self.dropout > 0, self._seed_buffer)
         self._last_streams = s
         return s
 

@@ -170,6 +170,42 @@ def gather_reduce_(csrs: Sequence[CSR], xs: Sequence[torch.Tensor], row_scales, 
     return out
 
 
+# ---- tensor-core (dense adjacency) formulation of the aggregation, tf32 mode only ---------------------------------------
+def _dense_of(rel: Relation, d: int):
+    return rel.dense(d) if PRECISION == "tf32" else None
+
+
+def _adj_times_table(dn, table, scale, out, accumulate):
+    """out[n_big, d] (+)= D @ (table * scale[:, None])   -- D [n_big, pad], table [n_small, d]"""
+    lib = _lib.load()
+    d = table.shape[1]
+    wt = torch.empty((d, dn.pad), dtype=torch.float32, device=table.device)
+    _run("b2g_transpose_pad", lib.b2g_transpose_pad, table.data_ptr(), _ptr(scale), table.shape[0], d, dn.pad, wt.data_ptr(), _stream())
+    cost(4 * (dn.n_big * dn.pad + d * dn.pad + dn.n_big * d * (2 if accumulate else 1)), 2 * dn.n_big * d * dn.pad)
+    _run("b2g_adjacency_mma_fwd", lib.b2g_linear_fwd_tc, dn.mat.data_ptr(), wt.data_ptr(), None, dn.n_big, d, dn.pad, out.data_ptr(),
+         int(accumulate), _stream())
+    return out
+
+
+def _adjT_times_rows(dn, x_big):
+    """(D^T @ x_big)[:n_small]  -> [n_small, d] view of a [pad, d] buffer"""
+    lib = _lib.load()
+    d = x_big.shape[1]
+    tmp = torch.empty((dn.pad, d), dtype=torch.float32, device=x_big.device)
+    ws = workspace(lib.b2g_linear_bwd_weight_tc_ws_bytes(dn.n_big, dn.pad, d), x_big.device)
+    cost(4 * (dn.n_big * dn.pad + dn.n_big * d + dn.pad * d), 2 * dn.n_big * d * dn.pad)
+    _run("b2g_adjacency_mma_bwd", lib.b2g_linear_bwd_weight_tc, dn.mat.data_ptr(), x_big.data_ptr(), dn.n_big, dn.pad, d, tmp.data_ptr(),
+         ws.data_ptr(), ws.numel(), _stream())
+    return tmp[:dn.n_small]
+
+
+def _row_scale(x, scale):
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    _run("b2g_row_scale", lib.b2g_row_scale, x.data_ptr(), scale.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), _stream())
+    return out
+
+
 def dropout_mask(n: int, p: float, seed: int, stream_id: int, device) -> torch.Tensor:
     """The keep mask (0 or 1/(1-p)) the kernels apply for (seed, stream_id) -- for replay on the CPU oracle."""
     lib = _lib.load()
@@ -352,20 +388,31 @@ class L2NormFn(Function):
 
 class MeanAggFn(Function):
     """agg[v] = mean_{u -> v} x_src[u]  with count clamped to >= 1  (PyG SAGEConv(aggr='mean').propagate,
-    called from model.py:256).  Backward walks the transposed CSR: no float atomics."""
+    called from model.py:256).  Backward walks the transposed CSR: no float atomics.  In tf32 mode dense-enough
+    relations use the tensor-core formulation on the dense adjacency (see b2g.h)."""
 
     @staticmethod
     def forward(ctx, x_src, rel: Relation):
         x_src = _f32(x_src, "x_src")
+        dn = _dense_of(rel, x_src.shape[1])
+        ctx.rel, ctx.dn = rel, dn
+        if dn is not None and not dn.big_is_dst:          # many sources -> few destinations: diag(1/deg_dst) D^T x_src
+            return _row_scale(_adjT_times_rows(dn, x_src), rel.by_dst.inv_deg)
         out = torch.empty((rel.n_dst, x_src.shape[1]), dtype=torch.float32, device=x_src.device)
+        if dn is not None:                                # few sources -> many destinations: D' x_src
+            return _adj_times_table(dn, x_src, None, out, False)
         gather_reduce_([rel.by_dst], [x_src], [rel.by_dst.inv_deg], [None], out, False)
-        ctx.rel = rel
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        rel = ctx.rel
+        rel, dn = ctx.rel, ctx.dn
         dout = _f32(dout, "grad")
+        if dn is not None and not dn.big_is_dst:          # dx_src = D (dout / deg_dst)
+            dx = torch.empty((rel.n_src, dout.shape[1]), dtype=torch.float32, device=dout.device)
+            return _adj_times_table(dn, dout, rel.by_dst.inv_deg, dx, False), None
+        if dn is not None:                                # dx_src = D'^T dout
+            return _adjT_times_rows(dn, dout), None
         dx = torch.empty((rel.n_src, dout.shape[1]), dtype=torch.float32, device=dout.device)
         gather_reduce_([rel.by_src], [dout], [None], [rel.by_dst.inv_deg], dx, False)
         return dx, None
@@ -394,8 +441,17 @@ class SageDstFn(Function):
         linear_fwd_(x_dst, w_root, b_root, out)
         for agg, wl in zip(aggs, wls):
             linear_fwd_(agg, wl, None, out, accumulate=True)
-        if n_small:
-            gather_reduce_([r.by_dst for r in small_rels], ys, [r.by_dst.inv_deg for r in small_rels], [None] * n_small, out, True)
+        d = out.shape[1]
+        dense = [_dense_of(r, d) for r in small_rels]
+        dense = [dn if (dn is not None and dn.big_is_dst) else None for dn in dense]
+        for r, y, dn in zip(small_rels, ys, dense):
+            if dn is not None:
+                _adj_times_table(dn, y, None, out, True)
+        rest = [i for i, dn in enumerate(dense) if dn is None]
+        if rest:
+            gather_reduce_([small_rels[i].by_dst for i in rest], [ys[i] for i in rest], [small_rels[i].by_dst.inv_deg for i in rest],
+                           [None] * len(rest), out, True)
+        ctx.dense = dense
         ctx.save_for_backward(x_dst, w_root, *aggs, *wls)
         ctx.meta = (small_rels, n_big, b_root is not None, [y.shape for y in ys])
         return out
@@ -421,6 +477,9 @@ class SageDstFn(Function):
         d_ys: List[Optional[torch.Tensor]] = []
         for k, rel in enumerate(small_rels):
             if nig[5 + k]:
+                if ctx.dense[k] is not None:
+                    d_ys.append(_adjT_times_rows(ctx.dense[k], dout))
+                    continue
                 dy = torch.empty(y_shapes[k], dtype=torch.float32, device=dout.device)
                 gather_reduce_([rel.by_src], [dout], [None], [rel.by_dst.inv_deg], dy, False)
                 d_ys.append(dy)

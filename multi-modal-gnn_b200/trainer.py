@@ -14,7 +14,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .model import compute_regression_loss
 
 
@@ -117,6 +117,9 @@ class Trainer:
         self.best_val_loss, self.patience_counter = float("inf"), 0
         self.train_losses, self.val_losses = [], []
         self.lab_weights = self._compute_lab_weights()
+        self.grad_hook = None          # called between backward and optimizer.step (multi-GPU gradient all-reduce)
+        self._use_graph, self._graph = False, None
+        self.graph_kernel_nodes = 0
 
     def _build_optimizer(self, oc):
         kind = oc.get("type", "adam").lower()
@@ -142,15 +145,73 @@ class Trainer:
         ei, ev = self.masker.split_edges("train")
         return compute_lab_weights(ei[1], ev, int(self.data["lab"].num_nodes))
 
+    # ---- CUDA graph mode ------------------------------------------------------------------------------------------
+    def enable_cuda_graph(self, enabled: bool = True):
+        """Capture forward + loss + backward of the training step into one CUDA graph (the step is ~270 short launches
+        and host-bound when issued one by one).  The graph is captured on the first train_step for a given set of
+        index / target tensors and replayed afterwards; the supervision mask and the dropout seed are refreshed in
+        static device buffers before every replay; the optimizer step stays eager."""
+        self._use_graph = bool(enabled)
+        self._graph = None
+
+    def _loss_of(self, pred, edge_values, lab_indices, sup):
+        if self.loss_fn in ("mae", "mse"):
+            return ops.weighted_loss(pred, edge_values, lab_indices, self.lab_weights, sup, self.loss_fn)
+        return ops.weighted_loss(pred, edge_values, None, None, sup, self.loss_fn)   # train.py:378-383
+
+    def _capture(self, pi, li, ev, sup):
+        model, dev = self.model, self.device
+        model._seed_buffer = torch.zeros(1, dtype=torch.int64, device=dev)
+        sup_static = torch.empty_like(sup)
+        sup_static.copy_(sup)
+        model._seed_buffer.fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
+        buffers = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up: allocations, caches, lazy attributes
+            for _ in range(2):
+                self.optimizer.zero_grad(set_to_none=True)
+                self._loss_of(model.predict_lab_values(self.data, pi, li), ev, li, sup_static).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.no_grad():                               # the warm-up must not count as training steps
+            sd = model.state_dict()
+            for k, v in buffers.items():
+                sd[k].copy_(v)
+        self.optimizer.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        lib = _lib.load()
+        before = int(lib.b2g_launch_count())
+        with torch.cuda.graph(graph):
+            loss = self._loss_of(model.predict_lab_values(self.data, pi, li), ev, li, sup_static)
+            loss.backward()
+        self.graph_kernel_nodes = int(lib.b2g_launch_count()) - before      # libb2g kernels replayed per step
+        with torch.no_grad():                               # capture does not execute; make sure buffers are unchanged
+            for k, v in buffers.items():
+                sd[k].copy_(v)
+        self._graph = {"graph": graph, "loss": loss, "sup": sup_static, "key": (id(pi), id(li), id(ev)), "refs": (pi, li, ev)}
+
+    def _graph_step(self, pi, li, ev, sup):
+        if self._graph is None or self._graph["key"] != (id(pi), id(li), id(ev)):
+            self._capture(pi, li, ev, sup)
+        g = self._graph
+        g["sup"].copy_(sup, non_blocking=True)
+        self.model._seed_buffer.fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
+        g["graph"].replay()
+        if self.grad_hook is not None:
+            self.grad_hook()
+        self.optimizer.step()
+        return g["loss"]
+
     def train_step(self, patient_indices, lab_indices, edge_values, supervision_mask) -> torch.Tensor:
         """Body of train_epoch (train.py:356-390) on device tensors; returns the loss tensor (no host sync)."""
+        if getattr(self, "_use_graph", False) and self.model.training:
+            return self._graph_step(patient_indices, lab_indices, edge_values, supervision_mask)
         self.optimizer.zero_grad()
         pred = self.model.predict_lab_values(self.data, patient_indices, lab_indices)
-        if self.loss_fn in ("mae", "mse"):
-            loss = ops.weighted_loss(pred, edge_values, lab_indices, self.lab_weights, supervision_mask, self.loss_fn)
-        else:   # train.py:378-383: unweighted fallback over the supervised subset
-            loss = ops.weighted_loss(pred, edge_values, None, None, supervision_mask, self.loss_fn)
+        loss = self._loss_of(pred, edge_values, lab_indices, supervision_mask)
         loss.backward()
+        if self.grad_hook is not None:
+            self.grad_hook()
         self.optimizer.step()
         return loss
 

@@ -657,3 +657,87 @@ def test_tcgen05_weight_gradient(m, n, k, dev):
     ws2 = torch.empty(lib.b2g_bn_ws_bytes(n), dtype=torch.uint8, device=dev)
     L.check(lib.b2g_col_sums(dy2.data_ptr(), m, n, db.data_ptr(), ws2.data_ptr(), ws2.numel(), None))
     assert relerr(db, dy2.double().sum(0)) <= 1e-6
+
+
+def test_dense_adjacency_tensor_core_aggregation(dev):
+    """tf32 mode: the four products of a relation on tcgen05 with the dense adjacency, against the oracle's
+    index_select/index_add mean (fp64).  Entries of the adjacency are exact; the features are rounded to TF32."""
+    pkg, G, ops, M, T, L = _mods()
+    ops.set_precision("tf32")
+    spec = pkg.synth.GraphSpec("mid", 6000, 50, 114, 100, 200_000, 17_000, 52_000, low_degree_frac=0.05)
+    g = pkg.synth.make_graph(spec, seed=1)
+    gi = G.GraphIndex(pkg.synth.make_graph(spec, seed=1).to(dev))
+    gen = torch.Generator().manual_seed(0)
+    used = 0
+    for et in g.edge_types:
+        rel = gi.relations[et]
+        dn = rel.dense(128)
+        if dn is None:
+            continue
+        used += 1
+        ei = g[et].edge_index
+        dense_ref = torch.zeros(dn.n_big, dn.pad)
+        big, small = (ei[1], ei[0]) if dn.big_is_dst else (ei[0], ei[1])
+        dense_ref[big, small] = 1.0
+        if dn.big_is_dst:
+            dense_ref = dense_ref / torch.bincount(big, minlength=dn.n_big).clamp(min=1).float().unsqueeze(1)
+        torch.testing.assert_close(dn.mat.cpu(), dense_ref, rtol=0, atol=0)      # adjacency itself: exact
+        x = torch.randn(rel.n_src, 128, generator=gen)
+        go = torch.randn(rel.n_dst, 128, generator=gen)
+        xr = x.double().requires_grad_(True)
+        ref = R.mean_aggregate(xr, ei, rel.n_dst)
+        ref.backward(go.double())
+        xd = x.to(dev).requires_grad_(True)
+        ops.PROFILE = []
+        out = ops.MeanAggFn.apply(xd, rel)
+        out.backward(go.to(dev))
+        names = {p[0] for p in ops.PROFILE}
+        ops.PROFILE = None
+        assert {"b2g_adjacency_mma_fwd", "b2g_adjacency_mma_bwd"} <= names, names
+        assert relerr(out, ref.detach()) <= 2e-3, et
+        assert relerr(xd.grad, xr.grad) <= 2e-3, et
+    assert used >= 4, "the mid-size graph should qualify lab and medication relations in both directions"
+
+
+def test_cuda_graph_step_equals_eager_step(dev):
+    """Trainer.enable_cuda_graph(): replaying the captured forward+loss+backward gives bit-identical losses and
+    parameters to issuing the same launches one by one (dropout 0), and fresh dropout masks per replay (dropout > 0)."""
+    pkg, G, ops, M, T, L = _mods()
+    g = pkg.synth.make_graph("tiny", seed=4)
+    counts = {nt: int(g[nt].num_nodes) for nt in g.node_types}
+    sd = R.init_state(counts, list(g.edge_types), seed=8)
+
+    def run(use_graph, dropout):
+        cfg = {"model": {"architecture": "RGCN", "hidden_dim": 128, "num_layers": 2, "dropout": dropout, "use_batch_norm": True,
+                         "activation": "relu"},
+               "train": {"loss": "mse", "epochs": 5, "early_stopping_patience": 15,
+                         "optimizer": {"type": "adam", "lr": 1e-3, "weight_decay": 1e-5}, "lr_scheduler": {"enabled": False}}}
+        model = M.build_model(cfg, (g.node_types, g.edge_types), None)
+        masker = T.EdgeMasker(pkg.synth.make_graph("tiny", seed=4), 0.7, 0.15, 0.15, 0.2, 42)
+        trainer = T.Trainer(model, masker.data, masker, cfg, dev)
+        model._init_embeddings(trainer.data)
+        model.load_state_dict(sd)
+        if use_graph:
+            trainer.enable_cuda_graph()
+        losses = [trainer.train_epoch(seed=500 + i) for i in range(4)]
+        return losses, {k: v.detach().clone() for k, v in model.state_dict().items()}, trainer
+
+    le, se, _ = run(False, 0.0)
+    lg, sg, tg = run(True, 0.0)
+    assert le == lg, (le, lg)
+    for k in se:
+        assert torch.equal(se[k], sg[k]), k
+    assert tg._graph is not None
+    assert int(sg["patient_transform.1.num_batches_tracked"]) == 8 and int(sg["batch_norms.0.lab.num_batches_tracked"]) == 4
+    # dropout > 0: every replay must see a new mask (the seed lives in device memory)
+    ld, _, td = run(True, 0.2)
+    assert all(torch.isfinite(torch.tensor(ld))) and len(set(ld)) == 4
+    with torch.no_grad():
+        pi, li = td.masker.split_rows("train")
+        td.model.train()
+        a = td.model.predict_lab_values(td.data, pi, li)
+        td.model._seed_buffer.fill_(12345)
+        b = td.model.predict_lab_values(td.data, pi, li)
+        td.model._seed_buffer.fill_(12345)
+        c = td.model.predict_lab_values(td.data, pi, li)
+    assert not torch.equal(a, b) and torch.equal(b, c)
