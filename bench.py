@@ -183,20 +183,27 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=90))
 
     spec = pkg.synth.SPECS[args.workload]
     cfg = _cfg(dropout=0.2, loss="mse")
-    # weak scaling: every rank owns an independent patient partition of the same shape (replicated type tables);
-    # see DESIGN.md section Multi-GPU for what is and is not synchronised in this round.
+    # Weak scaling over patients: every rank owns a patient partition of the same shape (its own
+    # patients, edges and train pairs; seed differs per rank) of ONE global graph whose lab / diagnosis / medication nodes,
+    # dense weights and BatchNorm parameters are replicated.  The exact mode is used: partial type sums, patient
+    # BatchNorm statistics and replicated->local gradients are all-reduced so that N ranks compute what one GPU would
+    # compute on the union graph (checked by tools/dist_check.py), plus one flat gradient all-reduce per step.
+    D = importlib.import_module(PKG + ".dist")
+    dctx = D.DistContext() if world > 1 else None
     g_host = pkg.synth.make_graph(spec, seed=42 + rank)
-    masker = T.EdgeMasker(g_host, 0.7, 0.15, 0.15, 0.2, 42)
+    masker = T.EdgeMasker(g_host, 0.7, 0.15, 0.15, 0.2, 42 + rank)
+    torch.manual_seed(0)
     model = M.build_model(cfg, (g_host.node_types, g_host.edge_types), None)
-    trainer = T.Trainer(model, g_host, masker, cfg, dev)
+    trainer = T.Trainer(model, g_host, masker, cfg, dev, dist_ctx=dctx)
     model._init_embeddings(trainer.data)          # tables exist before the first timed step (lazy init is not timed)
     if world > 1:
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
+        for name, p in model.named_parameters():
+            if not name.startswith("embeddings.patient"):
+                dist.broadcast(p.data, 0)
 
     pi, li = masker.split_rows("train")
     _, ev = masker.split_edges("train")
@@ -206,20 +213,8 @@ def run_ours(args):
     sup_dev = [s.to(dev) for s in sup_host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def allreduce_grads():
-        """the only NCCL traffic of the step: one flat all-reduce of the gradient bucket (north_star)"""
-        grads = [p.grad for p in model.parameters() if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat)
-        flat /= world
-        off = 0
-        for g in grads:
-            n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g)); off += n
-
-    if world > 1:
-        trainer.grad_hook = allreduce_grads
-    if not args.no_graph:
+    use_graph = (not args.no_graph) and world == 1      # NCCL collectives inside the step: issued eagerly for N > 1
+    if use_graph:
         trainer.enable_cuda_graph()
 
     def step_device(i):
@@ -251,14 +246,14 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     launches = int(lib.b2g_launch_count())            # eager launches in the timed region ...
-    if not args.no_graph:
+    if use_graph:
         launches += trainer.graph_kernel_nodes * args.steps   # ... plus the libb2g kernel nodes of every graph replay
     step_ms = [s.elapsed_time(e) for s, e in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / args.steps
-    final_loss = float(loss.item())
+    final_loss = float(trainer.global_loss(loss).item())
 
     # ---- timed: end to end through the public Trainer API with host inputs ----
     # Per-step host input of Trainer.train_epoch is the supervision mask the host-side EdgeMasker draws for that epoch
@@ -290,13 +285,15 @@ def run_ours(args):
 
     # ---- one instrumented step: per-kernel CUDA-event durations -> dominant kernel + roofline ----
     roof, kernels = None, None
+    trainer.enable_cuda_graph(False)             # per-call events cannot live inside a captured graph
+    step_device(args.warmup)                     # (every rank runs these two steps: they contain collectives)
+    ops.PROFILE = []
+    flush.fill_(1)
+    step_device(args.warmup)
+    torch.cuda.synchronize()
+    if rank != 0:
+        ops.PROFILE = None
     if rank == 0:
-        trainer.enable_cuda_graph(False)         # per-call events cannot live inside a captured graph
-        step_device(args.warmup)
-        ops.PROFILE = []
-        flush.fill_(1)
-        step_device(args.warmup)
-        torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
         for name, s, e, nbytes, flops in prof:
@@ -324,9 +321,9 @@ def run_ours(args):
                 "config": {"workload": f"{args.workload}: {spec.n_patient} patients/{spec.n_lab} labs/{spec.n_dx} dx/{spec.n_med} meds, "
                                        f"{spec.e_lab}/{spec.e_dx}/{spec.e_med} edges per GPU, d=128, L=2, dropout 0.2, mse + lab weights, "
                                        f"{n_train} train pairs, 20% supervised, Adam",
-                           "step": "Trainer.train_step: predict_lab_values fwd + weighted loss + bwd" + (" (one CUDA graph replay)" if not args.no_graph else "") + " + Adam",
+                           "step": "Trainer.train_step: predict_lab_values fwd + weighted loss + bwd" + (" (one CUDA graph replay)" if use_graph else "") + " + Adam",
                            "l2": "flushed with a 256 MiB write before every timed step; per-step working set (>1 GB) also exceeds the 126 MB L2",
-                           "parallelism": f"patient-partitioned x{world}" if world > 1 else "single GPU"},
+                           "parallelism": (f"patient-partitioned x{world}, exact mode: {dctx.n_collectives // max(1, total_steps + e2e_steps + 2)} small all-reduces + 1 gradient all-reduce per step" if world > 1 else "single GPU")},
                 "e2e": {"value": edges_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels, "final_loss": final_loss,

@@ -172,6 +172,19 @@ int b2g_col_sums(const float* x, int64_t m, int d, float* out, void* ws, size_t 
 size_t b2g_bn_ws_bytes(int d);
 int b2g_bn_stats(const float* x, int64_t m, int d, float eps, float momentum, float* mean, float* rstd,
                  float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream);
+/* Patient-partitioned (multi-GPU) BatchNorm: local fp64 column totals sums[2*d] = {sum x, sum x^2} -> (caller all-reduces)
+ * -> mean / rstd from the GLOBAL totals and row count.  Backward likewise with {sum g, sum g*xhat}; m_total is the global
+ * row count used in dx = gamma*rstd*(g - sum_g/m_total - xhat*sum_gx/m_total). */
+int b2g_bn_local_sums(const float* x, int64_t m, int d, double* sums, void* ws, size_t ws_bytes, void* stream);
+int b2g_bn_finalize_sums(const double* sums, int64_t m_total, int d, float eps, float momentum, float* mean,
+                         float* rstd, float* running_mean, float* running_var, void* stream);
+int b2g_bn_bwd_local_sums(const float* x, const float* dy, int64_t m, int d, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, int relu, float p_drop, uint64_t seed,
+                          uint64_t stream_id, double* sums, void* ws, size_t ws_bytes, void* stream);
+int b2g_bn_bwd_from_sums(const float* x, const float* dy, int64_t m, int64_t m_total, int d, const float* mean,
+                         const float* rstd, const float* gamma, const float* beta, int relu, float p_drop,
+                         uint64_t seed, uint64_t stream_id, const double* sums, float* dx, float* dgamma,
+                         float* dbeta, void* stream);
 /* eval mode: mean = running_mean, rstd = 1/sqrt(running_var + eps) */
 int b2g_bn_eval_stats(const float* running_mean, const float* running_var, int d, float eps, float* mean,
                       float* rstd, void* stream);

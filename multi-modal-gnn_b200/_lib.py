@@ -108,6 +108,11 @@ _PROTOS = {
     "b2g_linear_bwd_weight": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "b2g_bn_ws_bytes": (c_size_t, [c_int]),
     "b2g_bn_stats": (c_int, [_P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "b2g_bn_local_sums": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P]),
+    "b2g_bn_finalize_sums": (c_int, [_P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
+    "b2g_bn_bwd_local_sums": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, _P, _P, c_size_t, _P]),
+    "b2g_bn_bwd_from_sums": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, _P, _P, _P,
+                                     _P, _P]),
     "b2g_bn_eval_stats": (c_int, [_P, _P, c_int, c_float, _P, _P, _P]),
     "b2g_bn_apply": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_bn_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, c_int, _P, _P, _P,

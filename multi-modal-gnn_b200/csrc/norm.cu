@@ -149,6 +149,40 @@ __global__ void __launch_bounds__(256) k_colsum_finalize(const double* __restric
   if (slice == 0 && c < d) out[c] = (float)s0;
 }
 
+
+// ---- split statistics for patient-partitioned (multi-GPU) BatchNorm: local totals -> all-reduce -> finalize ----------------
+__global__ void __launch_bounds__(256) k_col_totals(const double* __restrict__ partial, int n_part, int d, double* __restrict__ sums) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  double s0, s1;
+  reduce_partials(partial, n_part, d, c, slice, s0, s1);
+  if (slice != 0 || c >= d) return;
+  sums[c] = s0;
+  sums[d + c] = s1;
+}
+
+__global__ void k_bn_finalize_sums(const double* __restrict__ sums, double m, int d, float eps, float momentum, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ running_mean, float* __restrict__ running_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  double mu = sums[c] / m;
+  double var = sums[d + c] / m - mu * mu;
+  if (var < 0) var = 0;
+  mean[c] = (float)mu;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+  if (running_var) {
+    double unb = m > 1 ? var * (m / (m - 1)) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+__global__ void k_sums_to_float(const double* __restrict__ sums, int d, float* __restrict__ dbeta, float* __restrict__ dgamma) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  if (dbeta) dbeta[c] = (float)sums[c];
+  if (dgamma) dgamma[c] = (float)sums[d + c];
+}
+
 __global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __restrict__ rv, int d, float eps, float* __restrict__ mean,
                                 float* __restrict__ rstd) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -430,6 +464,71 @@ extern "C" int b2g_col_sums(const float* x, int64_t m, int d, float* out, void* 
   B2G_LAUNCH_CHECK();
   k_colsum_finalize<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, d, out);
   B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+
+/* Patient-partitioned BatchNorm (multi-GPU): each rank reduces its rows to fp64 column totals sums[2*d] = {sum x, sum x^2}
+ * (b2g_bn_local_sums), the ranks all-reduce them, and b2g_bn_finalize_sums turns the global totals + global row count
+ * into mean / rstd (+ running-stat update).  Backward: b2g_bn_bwd_local_sums gives {sum g, sum g*xhat}; after the
+ * all-reduce b2g_bn_bwd_from_sums writes dx (m_total = global row count) and dgamma / dbeta. */
+extern "C" int b2g_bn_local_sums(const float* x, int64_t m, int d, double* sums, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(x && sums && m > 0 && d_ok(d) && aligned16(x), "bn_local_sums: bad args");
+  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
+    set_error("bn_local_sums: workspace too small");
+    return B2G_EWS;
+  }
+  double* partial = (double*)ws;
+  int parts = col_parts(m, d);
+  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
+  k_col_partial<0><<<parts, 256, smem, st>>>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, partial);
+  B2G_LAUNCH_CHECK();
+  k_col_totals<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, d, sums);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_bn_finalize_sums(const double* sums, int64_t m_total, int d, float eps, float momentum, float* mean, float* rstd,
+                                    float* running_mean, float* running_var, void* stream_) {
+  B2G_CHECK_ARG(sums && mean && rstd && m_total > 0 && d > 0, "bn_finalize_sums: bad args");
+  k_bn_finalize_sums<<<(unsigned)ceil_div(d, 128), 128, 0, (cudaStream_t)stream_>>>(sums, (double)m_total, d, eps, momentum, mean, rstd,
+                                                                                 running_mean, running_var);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_bn_bwd_local_sums(const float* x, const float* dy, int64_t m, int d, const float* mean, const float* rstd,
+                                     const float* gamma, const float* beta, int relu, float p_drop, uint64_t seed, uint64_t stream_id,
+                                     double* sums, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(m > 0 && d_ok(d) && x && dy && mean && rstd && gamma && beta && sums, "bn_bwd_local_sums: bad args");
+  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
+    set_error("bn_bwd_local_sums: workspace too small");
+    return B2G_EWS;
+  }
+  double* partial = (double*)ws;
+  int parts = col_parts(m, d);
+  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
+  k_col_partial<1><<<parts, 256, smem, st>>>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, partial);
+  B2G_LAUNCH_CHECK();
+  k_col_totals<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, d, sums);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" int b2g_bn_bwd_from_sums(const float* x, const float* dy, int64_t m, int64_t m_total, int d, const float* mean,
+                                    const float* rstd, const float* gamma, const float* beta, int relu, float p_drop, uint64_t seed,
+                                    uint64_t stream_id, const double* sums, float* dx, float* dgamma, float* dbeta, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(m > 0 && m_total >= m && d_ok(d) && x && dy && mean && rstd && gamma && beta && sums && dx, "bn_bwd_from_sums: bad args");
+  int64_t n4 = m * d / 4;
+  k_bn_bwd_apply<<<ew_grid(n4), 256, 0, st>>>(x, dy, n4, m_total, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, 1, sums, dx);
+  B2G_LAUNCH_CHECK();
+  if (dgamma || dbeta) {
+    k_sums_to_float<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(sums, d, dbeta, dgamma);
+    B2G_LAUNCH_CHECK();
+  }
   return B2G_OK;
 }
 

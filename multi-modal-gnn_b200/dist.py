@@ -1,0 +1,203 @@
+"""Patient-partitioned multi-GPU execution.  One process per GPU, torch.distributed (NCCL over
+NVLink on the B200 box, gloo in the CPU tests) for the plumbing.
+
+Every edge of the graph is patient <-> {lab, diagnosis, medication}, so a contiguous patient range owns all of its
+edges, embedding rows, activations, prediction pairs and gradients; the type tables (<= 135 KB), all dense weights and
+BatchNorm parameters are replicated.  To reproduce the single-GPU (= reference, full-batch) numbers exactly the ranks
+exchange, all as fp32/fp64 SUM all-reduces of tiny buffers:
+
+  forward   per-layer partial neighbour sums onto the type nodes          [N_type, d]      (PartialToReplicatedFn)
+            patient BatchNorm statistics                                  [2, d] fp64      (ops.SyncBNActDropFn)
+  backward  gradients of replicated tensors consumed by rank-local work   [N_type, d|64]   (ReplicatedToLocalFn)
+            patient BatchNorm backward statistics                         [2, d] fp64
+  step      one flat gradient all-reduce                                  483,970 floats
+
+Replicated computations (everything on type rows) are executed identically on every rank; their parameters see the
+*full* gradient on every rank, so those uses are wrapped in ScaleGradFn(1/world) to make the final SUM all-reduce exact.
+The functions in this file are device-agnostic (they run on CPU tensors with gloo in tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+
+from .heterodata import HeteroGraph
+
+
+class DistContext:
+    def __init__(self, group=None, sharded_type: str = "patient"):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.sharded_type = sharded_type
+        self.global_rows: Dict[int, int] = {}      # local row count of the sharded type -> global row count
+        self.n_collectives = 0
+        self.trace = [] if __import__("os").environ.get("B2G_TRACE_COLLECTIVES") else None   # debugging aid
+
+    def all_reduce_(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
+        if self.trace is not None:
+            self.trace.append((self.n_collectives, tuple(t.shape), str(t.dtype)))
+        dist.all_reduce(t, op=op, group=self.group)
+        self.n_collectives += 1
+        return t
+
+    def global_row_count(self, local_rows: int, device) -> int:
+        """Number of rows of the sharded node type over all ranks (one tiny all-reduce, cached)."""
+        if local_rows not in self.global_rows:
+            t = torch.tensor([local_rows], dtype=torch.int64, device=device)
+            self.all_reduce_(t)
+            self.global_rows[local_rows] = int(t.item())
+        return self.global_rows[local_rows]
+
+
+class ReplicatedToLocalFn(Function):
+    """Identity in forward; in backward the gradient (each rank holds only its share) is summed over ranks, so that
+    the replicated producer sees the full gradient on every rank."""
+
+    @staticmethod
+    def forward(ctx, x, dctx: DistContext):
+        ctx.dctx = dctx
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        ctx.dctx.all_reduce_(g)
+        return g, None
+
+
+class PartialToReplicatedFn(Function):
+    """Sum of per-rank partial results in forward (every rank ends with the full tensor); identity in backward (the
+    gradient of a replicated tensor is already complete and identical on every rank)."""
+
+    @staticmethod
+    def forward(ctx, x, dctx: DistContext):
+        y = x.contiguous().clone()
+        dctx.all_reduce_(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class ScaleGradFn(Function):
+    @staticmethod
+    def forward(ctx, x, s: float):
+        ctx.s = s
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.s, None
+
+
+def replicated_to_local(x, dctx: Optional[DistContext]):
+    return x if dctx is None else ReplicatedToLocalFn.apply(x, dctx)
+
+
+def partial_to_replicated(x, dctx: Optional[DistContext]):
+    return x if dctx is None else PartialToReplicatedFn.apply(x, dctx)
+
+
+def rep_param(p, dctx: Optional[DistContext]):
+    """A parameter (or replicated leaf) used inside a computation that every rank repeats identically."""
+    return p if (dctx is None or p is None) else ScaleGradFn.apply(p, 1.0 / dctx.world)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def partition_bounds(data, world: int, sharded_type: str = "patient") -> torch.Tensor:
+    """Contiguous ranges of the sharded node type, balanced by incident-edge count.
+    Returns int64[world + 1] boundaries."""
+    n = int(data[sharded_type].num_nodes)
+    load = torch.ones(n, dtype=torch.float64)
+    for et, ei in data.edge_index_dict.items():
+        src, _, dst = et
+        if src == sharded_type:
+            load += torch.bincount(ei[0].cpu(), minlength=n).double()
+        if dst == sharded_type:
+            load += torch.bincount(ei[1].cpu(), minlength=n).double()
+    csum = load.cumsum(0)
+    targets = csum[-1] * torch.arange(1, world, dtype=torch.float64) / world
+    cuts = torch.searchsorted(csum, targets).clamp(1, n - 1) if world > 1 else torch.empty(0, dtype=torch.int64)
+    bounds = torch.cat([torch.zeros(1, dtype=torch.int64), cuts.long(), torch.tensor([n])])
+    return torch.cummax(bounds, 0)[0]
+
+
+def partition_graph(data, world: int, rank: int, sharded_type: str = "patient") -> Tuple[HeteroGraph, dict]:
+    """Local sub-graph of `rank`: its range of the sharded node type (ids relabelled to start at 0), every other node
+    type in full, and exactly the edges incident to its range, in their original relative order (so the CSR build and
+    the edge-level split masks stay consistent).  Returns (local graph, info) with info['edge_ids'][edge_type] = positions
+    of the kept edges in the global edge list and info['range'] = (p0, p1)."""
+    bounds = partition_bounds(data, world, sharded_type)
+    p0, p1 = int(bounds[rank]), int(bounds[rank + 1])
+    g = HeteroGraph()
+    for nt in data.node_types:
+        g[nt].num_nodes = (p1 - p0) if nt == sharded_type else int(data[nt].num_nodes)
+    info = {"range": (p0, p1), "bounds": bounds, "edge_ids": {}, "global_nodes": {nt: int(data[nt].num_nodes) for nt in data.node_types}}
+    for et in data.edge_types:
+        src, _, dst = et
+        ei = data[et].edge_index
+        keep = torch.ones(ei.shape[1], dtype=torch.bool, device=ei.device)
+        if src == sharded_type:
+            keep &= (ei[0] >= p0) & (ei[0] < p1)
+        if dst == sharded_type:
+            keep &= (ei[1] >= p0) & (ei[1] < p1)
+        ids = keep.nonzero().squeeze(1)
+        loc = ei[:, ids].clone()
+        if src == sharded_type:
+            loc[0] -= p0
+        if dst == sharded_type:
+            loc[1] -= p0
+        g[et].edge_index = loc.contiguous()
+        if "edge_attr" in data[et]:
+            g[et].edge_attr = data[et].edge_attr[ids].contiguous()
+        info["edge_ids"][tuple(et)] = ids
+    return g, info
+
+
+def globalize_degrees(graph_index, dctx: DistContext):
+    """Mean aggregation onto replicated node types divides by the GLOBAL neighbour count: all-reduce the per-type-node
+    degrees once and overwrite the local CSR's deg / inv_deg (integer all-reduce: exact)."""
+    if getattr(graph_index, "_globalized", False):
+        return
+    for et, rel in graph_index.relations.items():
+        if et[2] != dctx.sharded_type:
+            deg = rel.by_dst.deg.clone()
+            dctx.all_reduce_(deg)
+            rel.by_dst.deg = deg
+            rel.by_dst.inv_deg = 1.0 / deg.clamp(min=1).to(torch.float32)
+    graph_index._globalized = True
+
+
+def allreduce_gradients(params, dctx: DistContext):
+    """The step's gradient exchange: one flat SUM all-reduce.  Parameters whose gradient is None on every rank (dead
+    branches, SURVEY.md note N8) stay None so that Adam keeps skipping them like the reference does."""
+    params = list(params)
+    if not params:
+        return
+    dev = params[0].device
+    present = torch.tensor([0 if p.grad is None else 1 for p in params], dtype=torch.int32, device=dev)
+    dctx.all_reduce_(present, op=dist.ReduceOp.MAX)
+    present = present.tolist()
+    chunks = []
+    for p, has in zip(params, present):
+        if has:
+            chunks.append((p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1))
+    if not chunks:
+        return
+    flat = torch.cat(chunks)
+    dctx.all_reduce_(flat)
+    off = 0
+    for p, has in zip(params, present):
+        if has:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n

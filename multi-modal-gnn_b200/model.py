@@ -31,6 +31,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from .dist import DistContext, globalize_degrees, partial_to_replicated, rep_param, replicated_to_local
 from .graph import GraphIndex, PairIndex, graph_index, _stream
 
 EdgeType = Tuple[str, str, str]
@@ -61,14 +62,24 @@ class _DropoutStreams:
         return sid | self.flag
 
 
-def _bn_act_drop(x, bn: Optional[nn.BatchNorm1d], training: bool, act: int, p: float, streams: _DropoutStreams, tag: str):
+def _bn_act_drop(x, bn: Optional[nn.BatchNorm1d], training: bool, act: int, p: float, streams: _DropoutStreams, tag: str,
+                 dctx: Optional[DistContext] = None, sharded_rows: bool = False):
+    """dctx given: `sharded_rows` says whether x's rows are this rank's share of a partitioned node type (statistics are
+    all-reduced) or a replicated tensor (every rank repeats the computation; parameters see the full gradient)."""
     sid = streams.take(tag) if (training and p > 0) else 0
     if bn is None:
         return ops.ActDropFn.apply(x, act, p, streams.seed, sid, training)
     if training and bn.track_running_stats:
         bn.num_batches_tracked += 1
-    return ops.BNActDropFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, act, p, streams.seed, sid,
-                                 bn.eps, bn.momentum if bn.momentum is not None else 0.1)
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    if dctx is not None and sharded_rows and training:
+        m_total = dctx.global_row_count(x.shape[0], x.device)
+        return ops.SyncBNActDropFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, act, p, streams.seed, sid, bn.eps, mom,
+                                         dctx, m_total)
+    gamma, beta = bn.weight, bn.bias
+    if dctx is not None and not sharded_rows:
+        gamma, beta = rep_param(gamma, dctx), rep_param(beta, dctx)
+    return ops.BNActDropFn.apply(x, gamma, beta, bn.running_mean, bn.running_var, training, act, p, streams.seed, sid, bn.eps, mom)
 
 
 class EdgeRegressionHead(nn.Module):
@@ -109,7 +120,8 @@ class EdgeRegressionHead(nn.Module):
         h = ops.linear(edge_embeds, lins[0].weight, lins[0].bias)
         return self._tail(h, lins[1:], streams, "head")
 
-    def forward_pairs(self, h_p: torch.Tensor, h_l: torch.Tensor, pairs: PairIndex, streams: _DropoutStreams, tag: str):
+    def forward_pairs(self, h_p: torch.Tensor, h_l: torch.Tensor, pairs: PairIndex, streams: _DropoutStreams, tag: str,
+                      dctx: Optional[DistContext] = None):
         """Same function of cat([h_p[pi], h_l[li]], 1) (model.py:319-333) with the first layer factorised per
         node: U = h_p W[:, :d]^T on patients, V = h_l W[:, d:]^T + b on labs, z = relu(U[pi] + V[li])."""
         lins = self._linears()
@@ -118,7 +130,9 @@ class EdgeRegressionHead(nn.Module):
         d = h_p.shape[1]
         w0 = lins[0].weight
         u = ops.linear(h_p, w0[:, :d].contiguous(), None)
-        v = ops.linear(h_l, w0[:, d:].contiguous(), lins[0].bias)
+        # lab rows are replicated: every rank repeats this tiny product; its result is consumed by rank-local pairs
+        v = ops.linear(h_l, rep_param(w0[:, d:].contiguous(), dctx), rep_param(lins[0].bias, dctx))
+        v = replicated_to_local(v, dctx)
         if len(lins) == 3 and lins[1].weight.shape == (32, 64) and lins[2].weight.shape == (1, 32) and self.fused:
             drop = self.training and self.dropout_p > 0
             sid1 = streams.take(f"{tag}.drop0") if drop else 0
@@ -184,6 +198,7 @@ class HeteroRGCN(nn.Module):
         self._pair_plans: "OrderedDict[int, _PairPlan]" = OrderedDict()
         self._last_streams: Optional[_DropoutStreams] = None
         self._seed_buffer: Optional[torch.Tensor] = None      # set by Trainer.enable_cuda_graph()
+        self.dist: Optional[DistContext] = None               # set by set_distributed(): patient-partitioned multi-GPU
         self._register_load_state_dict_pre_hook(self._rename_pyg24_keys)
         logging.info(f"Initialized HeteroRGCN with hidden_dim={hidden_dim}, num_layers={num_layers}")
 
@@ -198,6 +213,11 @@ class HeteroRGCN(nn.Module):
 
     def _device(self):
         return next(self.parameters()).device
+
+    def set_distributed(self, dctx: Optional[DistContext]):
+        """Patient-partitioned execution (dist.py): `data` passed to forward / predict_lab_values is then this rank's
+        partition (its patients, all type nodes, its edges); results equal the single-GPU ones."""
+        self.dist = dctx
 
     def _init_embeddings(self, data):
         """model.py:180-204 -- idempotent; tables live on the module's device (fixes reference note N1)."""
@@ -216,13 +236,17 @@ class HeteroRGCN(nn.Module):
         """model.py:206-234.  embedding(arange(N)) is the table itself; patient rows go through
         Linear-BN-ReLU-Dropout x2, Linear, row L2 normalisation."""
         training = self.training
-        x = {nt: self.embeddings[nt].weight for nt in node_types}
+        dctx = self.dist
+        sharded = dctx.sharded_type if dctx is not None else None
+        x = {nt: (self.embeddings[nt].weight if (dctx is None or nt == sharded) else rep_param(self.embeddings[nt].weight, dctx))
+             for nt in node_types}
         if "patient" in x:
             pt = self.patient_transform
+            shard = sharded == "patient"
             h = ops.linear(x["patient"], pt[0].weight, pt[0].bias)
-            h = _bn_act_drop(h, pt[1], training, 1, self.dropout, streams, tag + ".drop0")
+            h = _bn_act_drop(h, pt[1], training, 1, self.dropout, streams, tag + ".drop0", dctx, shard)
             h = ops.linear(h, pt[4].weight, pt[4].bias)
-            h = _bn_act_drop(h, pt[5], training, 1, self.dropout, streams, tag + ".drop1")
+            h = _bn_act_drop(h, pt[5], training, 1, self.dropout, streams, tag + ".drop1", dctx, shard)
             h = ops.linear(h, pt[8].weight, pt[8].bias)
             x["patient"] = ops.L2NormFn.apply(h, 1e-12)
         return x
@@ -235,21 +259,34 @@ class HeteroRGCN(nn.Module):
         for et in self._edge_types:
             if et in gi.relations and et[0] in x and et[2] in x:
                 by_dst.setdefault(et[2], []).append(et)
+        dctx = self.dist
+        sharded = dctx.sharded_type if dctx is not None else None
         out = {}
         for dst, ets in by_dst.items():
+            # multi-GPU: rows of the sharded type are rank-local work; every other destination type is replicated work
+            rep = dctx if (dctx is not None and dst != sharded) else None
             w_root = b_root = None
             small_rels, ys, aggs, wls = [], [], [], []
             for et in ets:
                 conv = convs["__".join(et)]
-                w_root = conv.lin_r.weight if w_root is None else w_root + conv.lin_r.weight
-                b_root = conv.lin_l.bias if b_root is None else b_root + conv.lin_l.bias
+                w_r, b_l, w_l = rep_param(conv.lin_r.weight, rep), rep_param(conv.lin_l.bias, rep), conv.lin_l.weight
+                w_root = w_r if w_root is None else w_root + w_r
+                b_root = b_l if b_root is None else b_root + b_l
                 rel = gi.relations[et]
-                if rel.n_src < rel.n_dst:          # few sources: transform them first, then aggregate
+                src_replicated = dctx is not None and et[0] != sharded
+                partial_sources = rep is not None and not src_replicated    # this rank holds only some of the sources
+                if rel.n_src < rel.n_dst and not partial_sources:   # few sources: transform them first, then aggregate
                     small_rels.append(rel)
-                    ys.append(ops.linear(x[et[0]], conv.lin_l.weight, None))
+                    y = ops.linear(x[et[0]], rep_param(w_l, dctx if src_replicated else None), None)
+                    if src_replicated and rep is None:     # replicated table consumed by this rank's rows only
+                        y = replicated_to_local(y, dctx)
+                    ys.append(y)
                 else:                              # many sources: aggregate first, then transform
-                    aggs.append(ops.MeanAggFn.apply(x[et[0]], rel))
-                    wls.append(conv.lin_l.weight)
+                    agg = ops.MeanAggFn.apply(x[et[0]], rel)
+                    if partial_sources:            # partial mean over this rank's sources -> sum over ranks
+                        agg = partial_to_replicated(agg, dctx)
+                    aggs.append(agg)
+                    wls.append(rep_param(w_l, rep))
             out[dst] = ops.SageDstFn.apply(x[dst], w_root, b_root, tuple(small_rels), len(aggs), *ys, *aggs, *wls)
         return out
 
@@ -261,7 +298,8 @@ class HeteroRGCN(nn.Module):
             nx = {}
             for nt, v in x.items():
                 bn = self.batch_norms[layer][nt] if self.use_batch_norm else None
-                nx[nt] = _bn_act_drop(v, bn, training, self._act, p, streams, f"fwd.l{layer}.{nt}")
+                nx[nt] = _bn_act_drop(v, bn, training, self._act, p, streams, f"fwd.l{layer}.{nt}", self.dist,
+                                      self.dist is not None and nt == self.dist.sharded_type)
             x = nx
         return x
 
@@ -269,6 +307,12 @@ class HeteroRGCN(nn.Module):
         s = _DropoutStreams(self.training and self.dropout > 0, self._seed_buffer)
         self._last_streams = s
         return s
+
+    def _graph_index(self, data) -> GraphIndex:
+        gi = graph_index(data)
+        if self.dist is not None:
+            globalize_degrees(gi, self.dist)       # mean onto replicated types divides by the global neighbour count
+        return gi
 
     def _check_device(self):
         if self._device().type != "cuda":
@@ -287,7 +331,7 @@ class HeteroRGCN(nn.Module):
         self._check_device()
         if len(self.embeddings) == 0:
             self._init_embeddings(data)
-        gi = graph_index(data)
+        gi = self._graph_index(data)
         streams = self._streams()
         x = self._encode(list(data.node_types), streams, "fwd.enc")
         return self._gnn(x, gi, streams)
@@ -299,7 +343,7 @@ class HeteroRGCN(nn.Module):
             self._init_embeddings(data)
         if not patient_indices.is_cuda or not lab_indices.is_cuda:
             raise _lib.B2GError("patient_indices / lab_indices must be CUDA tensors")
-        gi = graph_index(data)
+        gi = self._graph_index(data)
         node_types = list(data.node_types)
         streams = self._streams()
         training = self.training
@@ -323,6 +367,8 @@ class HeteroRGCN(nn.Module):
         x = self._gnn(x0, gi, streams)
 
         plan = self._pair_plan(gi, patient_indices, lab_indices)
+        if self.dist is not None:
+            return self._predict_heads_distributed(plan, init, x, streams, patient_indices.device)
         outs = []
         if plan.low is not None:
             outs.append(self.tabular_mlp.forward_pairs(init["patient"], init["lab"], plan.low, streams, "tabular_mlp"))
@@ -333,6 +379,22 @@ class HeteroRGCN(nn.Module):
         if plan.idx_low is None:      # a single head covers every pair, already in caller order
             return outs[0]
         return _AssembleFn.apply(outs[0], outs[1], plan.idx_low, plan.idx_high, plan.m)
+
+    def _predict_heads_distributed(self, plan: "_PairPlan", init, x, streams, device):
+        """Multi-GPU: both heads run on EVERY rank, even when this rank has no pair for one of them, because their
+        replicated lab-side products carry a gradient all-reduce that all ranks must enter (a rank-dependent branch
+        around a collective deadlocks)."""
+        empty = plan.empty_pairs()
+        low = self.tabular_mlp.forward_pairs(init["patient"], init["lab"], plan.low if plan.low is not None else empty, streams,
+                                             "tabular_mlp", self.dist)
+        high = self.edge_predictor.forward_pairs(x["patient"], x["lab"], plan.high if plan.high is not None else empty, streams,
+                                                 "edge_predictor", self.dist)
+        if plan.idx_low is not None:
+            return _AssembleFn.apply(low, high, plan.idx_low, plan.idx_high, plan.m)
+        main, other = (high, low) if plan.high is not None else (low, high)
+        if plan.m == 0:
+            main = torch.zeros(0, dtype=torch.float32, device=device)
+        return main + 0.0 * (low.sum() + high.sum())       # keeps the unused head in the autograd graph (zero gradient)
 
     # ------------------------------------------------------------------------------------------
     def _pair_plan(self, gi: GraphIndex, pi: torch.Tensor, li: torch.Tensor) -> "_PairPlan":
@@ -379,6 +441,12 @@ class _PairPlan:
             self.idx_high = (~mask).nonzero().squeeze(1)
             self.low = PairIndex(pi64[self.idx_low], li64[self.idx_low], n_p, n_l)
             self.high = PairIndex(pi64[self.idx_high], li64[self.idx_high], n_p, n_l)
+
+    def empty_pairs(self) -> PairIndex:
+        if getattr(self, "_empty", None) is None:
+            e = torch.zeros(0, dtype=torch.int64, device=self.pi.device)
+            self._empty = PairIndex(e, e, self.gi.node_counts["patient"], self.gi.node_counts["lab"])
+        return self._empty
 
     def same_pairs(self, pi, li) -> bool:
         if pi is self.pi and li is self.li and (pi._version, li._version) == self.versions:

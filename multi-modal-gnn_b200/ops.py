@@ -298,6 +298,59 @@ class BNActDropFn(Function):
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
+class SyncBNActDropFn(Function):
+    """Training-mode BNActDropFn for a node type whose rows are partitioned over ranks (patients): the fp64 column
+    totals are all-reduced so that every rank normalises with the statistics of ALL rows (= the single-GPU result);
+    the backward all-reduces {sum g, sum g*xhat} the same way.  gamma/beta gradients are the global totals on every
+    rank, so they are returned divided by the world size (the step's gradient all-reduce sums them back)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, act, p_drop, seed, sid, eps, momentum, dctx, m_total):
+        lib = _lib.load()
+        x, gamma, beta = _f32(x, "x"), _f32(gamma, "bn.weight"), _f32(beta, "bn.bias")
+        m, d = x.shape
+        dev = x.device
+        sums = torch.empty(2 * d, dtype=torch.float64, device=dev)
+        ws = workspace(lib.b2g_bn_ws_bytes(d), dev)
+        cost(4 * m * d)
+        _run("b2g_bn_local_sums", lib.b2g_bn_local_sums, x.data_ptr(), m, d, sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        dctx.all_reduce_(sums)
+        mean = torch.empty(d, dtype=torch.float32, device=dev)
+        rstd = torch.empty(d, dtype=torch.float32, device=dev)
+        _run("b2g_bn_finalize_sums", lib.b2g_bn_finalize_sums, sums.data_ptr(), int(m_total), d, float(eps), float(momentum),
+             mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), _stream())
+        y = torch.empty_like(x)
+        cost(8 * m * d)
+        _run("b2g_bn_apply", lib.b2g_bn_apply, x.data_ptr(), m, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+             int(act), float(p_drop), int(seed), int(sid), y.data_ptr(), _stream())
+        ctx.save_for_backward(x, mean, rstd, gamma, beta)
+        ctx.cfg = (int(act), float(p_drop), int(seed), int(sid), dctx, int(m_total))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, mean, rstd, gamma, beta = ctx.saved_tensors
+        act, p, seed, sid, dctx, m_total = ctx.cfg
+        dy = _f32(dy, "grad")
+        m, d = x.shape
+        dev = x.device
+        sums = torch.empty(2 * d, dtype=torch.float64, device=dev)
+        ws = workspace(lib.b2g_bn_ws_bytes(d), dev)
+        cost(8 * m * d)
+        _run("b2g_bn_bwd_local_sums", lib.b2g_bn_bwd_local_sums, x.data_ptr(), dy.data_ptr(), m, d, mean.data_ptr(), rstd.data_ptr(),
+             gamma.data_ptr(), beta.data_ptr(), act, p, seed, sid, sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        dctx.all_reduce_(sums)
+        dx = torch.empty_like(x)
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+        cost(12 * m * d)
+        _run("b2g_bn_bwd_from_sums", lib.b2g_bn_bwd_from_sums, x.data_ptr(), dy.data_ptr(), m, m_total, d, mean.data_ptr(), rstd.data_ptr(),
+             gamma.data_ptr(), beta.data_ptr(), act, p, seed, sid, sums.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+             _stream())
+        inv = 1.0 / dctx.world
+        return dx, dgamma * inv, dbeta * inv, None, None, None, None, None, None, None, None, None, None
+
+
 class ActDropFn(Function):
     """dropout(act(x)) without normalisation (use_batch_norm=False branch of model.py:259-269)."""
 
@@ -567,6 +620,9 @@ class DecoderHeadFn(Function):
         dpred = _f32(dpred, "grad")
         dev = u.device
         m = pairs.m
+        if m == 0:      # a head without pairs on this rank: zero gradients (still returned, so collectives upstream stay matched)
+            return (torch.zeros_like(u), torch.zeros_like(v), torch.zeros_like(w2), torch.zeros_like(b2), torch.zeros_like(w3),
+                    torch.zeros(1, dtype=torch.float32, device=dev), None, None, None, None, None, None)
         g = torch.empty((m, 64), dtype=torch.float32, device=dev)
         flags = torch.empty(m, dtype=torch.float32, device=dev)
         dw2, db2, dw3 = torch.empty_like(w2), torch.empty_like(b2), torch.empty_like(w3)

@@ -15,6 +15,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib, ops
+from .dist import DistContext, allreduce_gradients
 from .model import compute_regression_loss
 
 
@@ -84,14 +85,20 @@ class EdgeMasker:
         return ei, ev, mask, sup
 
 
-def compute_lab_weights(lab_indices: torch.Tensor, edge_values: torch.Tensor, num_labs: int) -> torch.Tensor:
+def compute_lab_weights(lab_indices: torch.Tensor, edge_values: torch.Tensor, num_labs: int,
+                        dctx: Optional[DistContext] = None) -> torch.Tensor:
     """Trainer._compute_lab_weights (train.py:295-330): 1 / (unbiased variance + 1e-6) per lab over the
     train split (variance := 1 for labs with < 2 samples), rescaled to sum to num_labs.  One-off, O(E)."""
     v = edge_values.double()
     cnt = torch.zeros(num_labs, dtype=torch.float64, device=v.device).index_add_(0, lab_indices, torch.ones_like(v))
     s1 = torch.zeros(num_labs, dtype=torch.float64, device=v.device).index_add_(0, lab_indices, v)
+    if dctx is not None:               # patient-partitioned: the variance is over the train pairs of ALL ranks
+        dctx.all_reduce_(cnt)
+        dctx.all_reduce_(s1)
     mean = s1 / cnt.clamp(min=1)
     s2 = torch.zeros(num_labs, dtype=torch.float64, device=v.device).index_add_(0, lab_indices, (v - mean[lab_indices]) ** 2)
+    if dctx is not None:
+        dctx.all_reduce_(s2)
     var = torch.where(cnt > 1, s2 / (cnt - 1).clamp(min=1), torch.ones_like(s2))
     w = 1.0 / (var.float() + 1e-6)
     return w * num_labs / w.sum()
@@ -100,7 +107,11 @@ def compute_lab_weights(lab_indices: torch.Tensor, edge_values: torch.Tensor, nu
 class Trainer:
     """train.py:183-431 (optimizer/scheduler construction, lab weights, train_epoch, validate)."""
 
-    def __init__(self, model, data, masker: EdgeMasker, config: Dict, device: torch.device):
+    def __init__(self, model, data, masker: EdgeMasker, config: Dict, device: torch.device, dist_ctx: Optional[DistContext] = None):
+        """``dist_ctx``: patient-partitioned multi-GPU mode -- ``data`` / ``masker`` are this rank's partition (dist.py)."""
+        self.dist = dist_ctx
+        if dist_ctx is not None:
+            model.set_distributed(dist_ctx)
         self.model = model.to(device)
         self.data = data.to(device)
         self.masker = masker
@@ -117,7 +128,11 @@ class Trainer:
         self.best_val_loss, self.patience_counter = float("inf"), 0
         self.train_losses, self.val_losses = [], []
         self.lab_weights = self._compute_lab_weights()
-        self.grad_hook = None          # called between backward and optimizer.step (multi-GPU gradient all-reduce)
+        # called between backward and optimizer.step: the multi-GPU gradient all-reduce
+        # (the sharded node type's embedding rows are rank-local: their gradients are never exchanged)
+        self.grad_hook = (lambda: allreduce_gradients(
+            [p for n, p in self.model.named_parameters() if not n.startswith(f"embeddings.{self.dist.sharded_type}.")],
+            self.dist)) if self.dist is not None else None
         self._use_graph, self._graph = False, None
         self.graph_kernel_nodes = 0
 
@@ -143,7 +158,7 @@ class Trainer:
 
     def _compute_lab_weights(self) -> torch.Tensor:
         ei, ev = self.masker.split_edges("train")
-        return compute_lab_weights(ei[1], ev, int(self.data["lab"].num_nodes))
+        return compute_lab_weights(ei[1], ev, int(self.data["lab"].num_nodes), self.dist)
 
     # ---- CUDA graph mode ------------------------------------------------------------------------------------------
     def enable_cuda_graph(self, enabled: bool = True):
@@ -156,8 +171,21 @@ class Trainer:
 
     def _loss_of(self, pred, edge_values, lab_indices, sup):
         if self.loss_fn in ("mae", "mse"):
-            return ops.weighted_loss(pred, edge_values, lab_indices, self.lab_weights, sup, self.loss_fn)
-        return ops.weighted_loss(pred, edge_values, None, None, sup, self.loss_fn)   # train.py:378-383
+            loss = ops.weighted_loss(pred, edge_values, lab_indices, self.lab_weights, sup, self.loss_fn)
+        else:
+            loss = ops.weighted_loss(pred, edge_values, None, None, sup, self.loss_fn)   # train.py:378-383
+        if self.dist is not None:
+            # global mean over the supervised pairs of all ranks = sum_r (n_r / n) * local mean_r
+            n_local = sup.sum().to(torch.float32)
+            n_total = self.dist.all_reduce_(n_local.clone())
+            loss = torch.nan_to_num(loss) * (n_local / n_total)
+        return loss
+
+    def global_loss(self, loss: torch.Tensor) -> torch.Tensor:
+        """Loss of the whole (partitioned) batch: the per-rank terms of _loss_of summed over ranks."""
+        if self.dist is None:
+            return loss
+        return self.dist.all_reduce_(loss.detach().clone())
 
     def _capture(self, pi, li, ev, sup):
         model, dev = self.model, self.device
