@@ -179,10 +179,16 @@ def run_ours(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    # stdout must carry exactly one JSON line (rank 0): park fd 1 on stderr while libraries (NCCL's version banner) may
+    # print, restore it for the final line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=90))
 
     spec = pkg.synth.SPECS[args.workload]
@@ -213,7 +219,7 @@ def run_ours(args):
     sup_dev = [s.to(dev) for s in sup_host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    use_graph = (not args.no_graph) and world == 1      # NCCL collectives inside the step: issued eagerly for N > 1
+    use_graph = not args.no_graph        # for N > 1 the step's NCCL all-reduces are captured into the graph as well
     if use_graph:
         trainer.enable_cuda_graph()
 
@@ -331,6 +337,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             v, ms, sample, cores = cpu_baseline_run(args.workload, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -84,6 +84,43 @@ class PartialToReplicatedFn(Function):
         return g, None
 
 
+class PartialToReplicatedManyFn(Function):
+    """PartialToReplicatedFn for several tensors with ONE all-reduce (the three per-layer partial type sums)."""
+
+    @staticmethod
+    def forward(ctx, dctx: DistContext, *xs):
+        flat = torch.cat([x.reshape(-1) for x in xs])
+        dctx.all_reduce_(flat)
+        outs, off = [], 0
+        for x in xs:
+            outs.append(flat[off:off + x.numel()].view_as(x))
+            off += x.numel()
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        return (None, *gs)
+
+
+class ReplicatedToLocalManyFn(Function):
+    """ReplicatedToLocalFn for several tensors: their gradients are summed over ranks with ONE all-reduce."""
+
+    @staticmethod
+    def forward(ctx, dctx: DistContext, *xs):
+        ctx.dctx = dctx
+        return tuple(x.view_as(x) for x in xs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        flat = torch.cat([g.reshape(-1) for g in gs])
+        ctx.dctx.all_reduce_(flat)
+        outs, off = [], 0
+        for g in gs:
+            outs.append(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        return (None, *outs)
+
+
 class ScaleGradFn(Function):
     @staticmethod
     def forward(ctx, x, s: float):
@@ -101,6 +138,14 @@ def replicated_to_local(x, dctx: Optional[DistContext]):
 
 def partial_to_replicated(x, dctx: Optional[DistContext]):
     return x if dctx is None else PartialToReplicatedFn.apply(x, dctx)
+
+
+def partial_to_replicated_many(xs, dctx: Optional[DistContext]):
+    return list(xs) if (dctx is None or not xs) else list(PartialToReplicatedManyFn.apply(dctx, *xs))
+
+
+def replicated_to_local_many(xs, dctx: Optional[DistContext]):
+    return list(xs) if (dctx is None or not xs) else list(ReplicatedToLocalManyFn.apply(dctx, *xs))
 
 
 def rep_param(p, dctx: Optional[DistContext]):

@@ -31,7 +31,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .dist import DistContext, globalize_degrees, partial_to_replicated, rep_param, replicated_to_local
+from .dist import (DistContext, globalize_degrees, partial_to_replicated_many, rep_param, replicated_to_local,
+                   replicated_to_local_many)
 from .graph import GraphIndex, PairIndex, graph_index, _stream
 
 EdgeType = Tuple[str, str, str]
@@ -261,7 +262,9 @@ class HeteroRGCN(nn.Module):
                 by_dst.setdefault(et[2], []).append(et)
         dctx = self.dist
         sharded = dctx.sharded_type if dctx is not None else None
-        out = {}
+        # pass 1: per-relation products; multi-GPU tensors that need an exchange are collected so that each kind costs
+        # ONE all-reduce per layer (partial type sums in forward, replicated->local gradients in backward)
+        plans, partial_aggs, local_ys = {}, [], []
         for dst, ets in by_dst.items():
             # multi-GPU: rows of the sharded type are rank-local work; every other destination type is replicated work
             rep = dctx if (dctx is not None and dst != sharded) else None
@@ -279,14 +282,23 @@ class HeteroRGCN(nn.Module):
                     small_rels.append(rel)
                     y = ops.linear(x[et[0]], rep_param(w_l, dctx if src_replicated else None), None)
                     if src_replicated and rep is None:     # replicated table consumed by this rank's rows only
-                        y = replicated_to_local(y, dctx)
+                        local_ys.append((ys, len(ys)))
                     ys.append(y)
                 else:                              # many sources: aggregate first, then transform
                     agg = ops.MeanAggFn.apply(x[et[0]], rel)
                     if partial_sources:            # partial mean over this rank's sources -> sum over ranks
-                        agg = partial_to_replicated(agg, dctx)
+                        partial_aggs.append((aggs, len(aggs)))
                     aggs.append(agg)
                     wls.append(rep_param(w_l, rep))
+            plans[dst] = (w_root, b_root, small_rels, ys, aggs, wls)
+        if dctx is not None:
+            for (lst, i), t in zip(partial_aggs, partial_to_replicated_many([lst[i] for lst, i in partial_aggs], dctx)):
+                lst[i] = t
+            for (lst, i), t in zip(local_ys, replicated_to_local_many([lst[i] for lst, i in local_ys], dctx)):
+                lst[i] = t
+        # pass 2: one fused SageDstFn per destination type
+        out = {}
+        for dst, (w_root, b_root, small_rels, ys, aggs, wls) in plans.items():
             out[dst] = ops.SageDstFn.apply(x[dst], w_root, b_root, tuple(small_rels), len(aggs), *ys, *aggs, *wls)
         return out
 
