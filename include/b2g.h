@@ -224,6 +224,12 @@ int b2g_l2norm_bwd(const float* y, const float* dy, const float* inv_norm, int64
 int b2g_decoder_fwd(const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2,
                     const float* b2, const float* w3, const float* b3, int64_t m, float p_drop, uint64_t seed,
                     uint64_t sid1, uint64_t sid2, float* pred, void* stream);
+/* Same forward with the 64 -> 32 layer on tcgen05 (tf32 mode): each thread writes its pair's z1 row into a K-major
+ * SWIZZLE_128B shared-memory tile, one thread issues the MMAs (M = 128 pairs, N = 32, TF32 operands, fp32 TMEM
+ * accumulator), each thread reads its accumulator row back.  Identical dropout streams; ~1e-3 relative. */
+int b2g_decoder_fwd_tc(const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2,
+                       const float* b2, const float* w3, const float* b3, int64_t m, float p_drop, uint64_t seed,
+                       uint64_t sid1, uint64_t sid2, float* pred, void* stream);
 /* Backward of the above for upstream gradient dpred[M].  Pairs with dpred == 0 (the unsupervised 80 %,
  * train.py:366-368) are compacted away first (stable order -> deterministic sums).  Outputs: g_rows[M,64] = d loss /
  * d (U[p]+V[l]) written ONLY for pairs with dpred != 0; active_flags[M] = 1.0 / 0.0 marks those rows (pass it as
@@ -234,6 +240,13 @@ int b2g_decoder_bwd(const float* U, const float* V, const int64_t* pi, const int
                     const float* b2, const float* w3, const float* dpred, int64_t m, float p_drop, uint64_t seed,
                     uint64_t sid1, uint64_t sid2, float* g_rows, float* active_flags, float* dW2, float* db2,
                     float* dw3, float* db3, void* ws, size_t ws_bytes, void* stream);
+
+/* tf32-mode backward: per 128-pair tile both contractions (a2 = z1 W2^T, dz1 = da2 W2) run on tcgen05 from thread-written
+ * swizzled shared-memory tiles; dW2 is accumulated from the same tiles with fp32 FMAs.  Same arguments / outputs. */
+int b2g_decoder_bwd_tc(const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2,
+                       const float* b2, const float* w3, const float* dpred, int64_t m, float p_drop, uint64_t seed,
+                       uint64_t sid1, uint64_t sid2, float* g_rows, float* active_flags, float* dW2, float* db2,
+                       float* dw3, float* db3, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (f) loss -- train.py:364-386 weighted MAE / MSE over the supervised subset, model.py:602-605

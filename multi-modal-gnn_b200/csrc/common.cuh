@@ -100,17 +100,33 @@ __device__ __forceinline__ void resolve_seed(uint64_t& seed, uint64_t& sid) {
   }
 }
 
-// keep-scale for 4 consecutive elements starting at element index 4*quad of dropout stream `sid`
+// Dropout keep-scales.  One Philox4x32-10 call yields 128 random bits = eight 16-bit uniforms; element e of dropout
+// stream `sid` uses call counter e / 8 and 16-bit lane e % 8, and is dropped when its uniform is below
+// floor(p * 65536) (keep probability quantised to 2^-16: relative error <= 1.6e-5 at p = 0.2).
+__device__ __forceinline__ void dropout_scale8(uint64_t seed, uint64_t sid, uint64_t oct, float p, float (&m)[8]) {
+  Philox ph(seed);
+  uint4 r = ph(oct, sid);
+  const float inv = 1.0f / (1.0f - p);
+  const uint32_t thr = (uint32_t)(p * 65536.0f);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[2 * i] = ((w[i] & 0xffffu) >= thr) ? inv : 0.f;
+    m[2 * i + 1] = ((w[i] >> 16) >= thr) ? inv : 0.f;
+  }
+}
+// keep-scale for the 4 consecutive elements 4*quad .. 4*quad+3 (half of one Philox call)
 __device__ __forceinline__ float4 dropout_scale4(uint64_t seed, uint64_t sid, uint64_t quad, float p) {
   Philox ph(seed);
-  uint4 r = ph(quad, sid);
+  uint4 r = ph(quad >> 1, sid);
   const float inv = 1.0f / (1.0f - p);
-  const float u = 2.3283064365386963e-10f;  // 2^-32
+  const uint32_t thr = (uint32_t)(p * 65536.0f);
+  const uint32_t a = (quad & 1) ? r.z : r.x, b = (quad & 1) ? r.w : r.y;
   float4 m;
-  m.x = ((float)r.x * u >= p) ? inv : 0.f;
-  m.y = ((float)r.y * u >= p) ? inv : 0.f;
-  m.z = ((float)r.z * u >= p) ? inv : 0.f;
-  m.w = ((float)r.w * u >= p) ? inv : 0.f;
+  m.x = ((a & 0xffffu) >= thr) ? inv : 0.f;
+  m.y = ((a >> 16) >= thr) ? inv : 0.f;
+  m.z = ((b & 0xffffu) >= thr) ? inv : 0.f;
+  m.w = ((b >> 16) >= thr) ? inv : 0.f;
   return m;
 }
 // A row slice held by one lane: D/32 floats. D >= 128 -> float4 pieces at columns j*128 + lane*4 (every load

@@ -9,7 +9,7 @@
 // compacted away (stable, deterministic); each remaining pair recomputes its forward, writes its 64-wide
 // gradient row g (consumed by the per-patient / per-lab segmented reducers) and the CTA accumulates
 // dW2 / db2 / dw3 / db3 in registers across its tiles; a second stage adds the per-CTA partials in order.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 using namespace b2g;
@@ -23,14 +23,17 @@ __device__ __forceinline__ void load_z1(const float* __restrict__ U, const float
   const float4* u4 = reinterpret_cast<const float4*>(U + (size_t)p * H1);
   const float4* v4 = reinterpret_cast<const float4*>(V + (size_t)l * H1);
 #pragma unroll
-  for (int q = 0; q < H1 / 4; ++q) {
-    float4 a = __ldg(u4 + q), b = __ldg(v4 + q);
-    float4 r = make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
-    if (p_drop > 0.f) {
-      float4 mk = dropout_scale4(seed, sid1, (uint64_t)pair * (H1 / 4) + q, p_drop);
-      r.x *= mk.x; r.y *= mk.y; r.z *= mk.z; r.w *= mk.w;
+  for (int o = 0; o < H1 / 8; ++o) {          // 8 elements = one Philox call
+    float mk[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (p_drop > 0.f) dropout_scale8(seed, sid1, (uint64_t)pair * (H1 / 8) + o, p_drop, mk);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 a = __ldg(u4 + 2 * o + h), b = __ldg(v4 + 2 * o + h);
+      z[8 * o + 4 * h + 0] = fmaxf(a.x + b.x, 0.f) * mk[4 * h + 0];
+      z[8 * o + 4 * h + 1] = fmaxf(a.y + b.y, 0.f) * mk[4 * h + 1];
+      z[8 * o + 4 * h + 2] = fmaxf(a.z + b.z, 0.f) * mk[4 * h + 2];
+      z[8 * o + 4 * h + 3] = fmaxf(a.w + b.w, 0.f) * mk[4 * h + 3];
     }
-    z[4 * q] = r.x; z[4 * q + 1] = r.y; z[4 * q + 2] = r.z; z[4 * q + 3] = r.w;
   }
 }
 
@@ -86,6 +89,118 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) k_decoder_fwd(const float* __r
       out = fmaf(sw3[jg * 4 + 3], fmaxf(a[3], 0.f) * mk.w, out);
     }
     pred[i] = out;
+  }
+}
+
+// ---- tensor-core forward (tf32 mode) ----------------------------------------------------------------------------------
+// Same function as k_decoder_fwd, but the 64 -> 32 layer of a 128-pair tile runs on tcgen05: every thread gathers its
+// pair's z1 row and writes it straight into a K-major SWIZZLE_128B shared-memory tile (row = pair, 2 x 128 B), one
+// thread issues 8 tcgen05.mma (M = 128 pairs, N = 32, K = 8, TF32 operands, fp32 accumulation in TMEM), and every
+// thread reads its own accumulator row back (TMEM lane = pair) for bias / ReLU / dropout / the 32 -> 1 dot product.
+// 128 threads per CTA, ~40 KB of shared memory and 32 TMEM columns, so several CTAs share an SM and hide the gathers.
+constexpr int TCD_THREADS = 128;
+
+// byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] SWIZZLE_128B sub-tile
+__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+
+__global__ void __launch_bounds__(TCD_THREADS) k_decoder_fwd_tc(const float* __restrict__ U, const float* __restrict__ V,
+                                                               const int64_t* __restrict__ pi, const int64_t* __restrict__ li,
+                                                               const float* __restrict__ W2, const float* __restrict__ b2,
+                                                               const float* __restrict__ w3, const float* __restrict__ b3, int64_t M,
+                                                               float p_drop, uint64_t seed, uint64_t sid1, uint64_t sid2,
+                                                               float* __restrict__ pred) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sb2[H2], sw3[H2];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* base = dsm + ((1024u - (smem_u32(dsm) & 1023u)) & 1023u);
+  uint8_t* sZ = base;                 // 2 sub-tiles [128 rows x 128 B]   = 32 KB   (z1: A operand)
+  uint8_t* sW = base + 2 * 16384;     // 2 sub-tiles [ 32 rows x 128 B]   =  8 KB   (W2: B operand, N = 32 rows, K-major)
+
+  // W2 [32][64] -> swizzled K-major tile (once per CTA)
+  for (int i = tid; i < H2 * (H1 / 4); i += TCD_THREADS) {
+    const int n = i / (H1 / 4), c16 = i % (H1 / 4);              // row n, 16-byte chunk c16 (0..15) of its 64 floats
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W2 + n * H1) + c16);
+    *reinterpret_cast<float4*>(sW + (c16 >> 3) * 4096 + sw128(n, c16 & 7)) = w;
+  }
+  if (tid < H2) {
+    sb2[tid] = b2[tid];
+    sw3[tid] = w3[tid];
+  }
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(32));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  if (p_drop > 0.f) {
+    resolve_seed(seed, sid1);
+    sid2 &= ~SEED_IS_POINTER;
+  }
+  const float bias3 = __ldg(b3);
+  const uint32_t idesc = make_idesc(H2);
+  const uint32_t za = smem_u32(sZ), wa = smem_u32(sW);
+  const int64_t n_tiles = (M + TILE_M - 1) / TILE_M;
+  uint32_t phase = 0;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t i = t * TILE_M + tid;
+    const bool live = i < M;
+    {  // z1 row of this thread's pair -> swizzled A tile
+      float z[H1];
+      if (live) {
+        load_z1(U, V, __ldg(pi + i), __ldg(li + i), p_drop, seed, sid1, i, z);
+      } else {
+#pragma unroll
+        for (int k = 0; k < H1; ++k) z[k] = 0.f;
+      }
+#pragma unroll
+      for (int c16 = 0; c16 < H1 / 4; ++c16)
+        *reinterpret_cast<float4*>(sZ + (c16 >> 3) * 16384 + sw128(tid, c16 & 7)) =
+            make_float4(z[4 * c16], z[4 * c16 + 1], z[4 * c16 + 2], z[4 * c16 + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); // (and order the previous tile's TMEM reads)
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8)
+          umma_tf32(tmem_base, make_desc(za + kb * 16384 + k8 * 32), make_desc(wa + kb * 4096 + k8 * 32), idesc, (kb | k8) != 0);
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (live) {
+      float out = bias3;
+#pragma unroll
+      for (int jg = 0; jg < H2 / 4; ++jg) {
+        float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p_drop > 0.f) mk = dropout_scale4(seed, sid2, (uint64_t)i * (H2 / 4) + jg, p_drop);
+        out = fmaf(sw3[jg * 4 + 0], fmaxf(__uint_as_float(r[jg * 4 + 0]) + sb2[jg * 4 + 0], 0.f) * mk.x, out);
+        out = fmaf(sw3[jg * 4 + 1], fmaxf(__uint_as_float(r[jg * 4 + 1]) + sb2[jg * 4 + 1], 0.f) * mk.y, out);
+        out = fmaf(sw3[jg * 4 + 2], fmaxf(__uint_as_float(r[jg * 4 + 2]) + sb2[jg * 4 + 2], 0.f) * mk.z, out);
+        out = fmaf(sw3[jg * 4 + 3], fmaxf(__uint_as_float(r[jg * 4 + 3]) + sb2[jg * 4 + 3], 0.f) * mk.w, out);
+      }
+      pred[i] = out;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32));
   }
 }
 
@@ -320,22 +435,229 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decoder_bwd(const float* __rest
   if (lane == 0) pw[2 * H2] = acc_b3;
 }
 
-__global__ void __launch_bounds__(256) k_decoder_bwd_final(const float* __restrict__ partial, int n_cta, float* __restrict__ dW2,
-                                                           float* __restrict__ db2, float* __restrict__ dw3, float* __restrict__ db3) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < H2 * H1) {
-    float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * PART_STRIDE + i];
-    dW2[i] = s;
-  } else if (i < H2 * H1 + 2 * H2 + 1) {
-    int r = i - H2 * H1;  // 0..31 db2, 32..63 dw3, 64 db3
-    float s = 0.f;
-    for (int c = 0; c < n_cta; ++c)
-      for (int w = 0; w < 8; ++w) s += partial[(size_t)c * PART_STRIDE + H2 * H1 + w * (2 * H2 + 1) + r];
-    if (r < H2) db2[r] = s;
-    else if (r < 2 * H2) dw3[r - H2] = s;
-    else db3[0] = s;
+// ---- tensor-core backward (tf32 mode) --------------------------------------------------------------------------------
+// Per 128-pair tile (thread = pair, active pairs only):  z1 -> smem A tile;  MMA1: a2 = z1 W2^T (TMEM cols 0..31);
+// threads turn a2 into da2 and write it as a second A tile;  MMA2: dz1 = da2 W2 (TMEM cols 32..95, B = W2^T held K-major);
+// threads mask dz1 and store the gradient row g.  dW2 += da2^T z1 is accumulated from the two shared-memory tiles with
+// fp32 FMAs while MMA2 runs (the only SIMT contraction left); column sums for db2 / dw3 / db3 by warp shuffles.
+constexpr int PART_TC = H2 * H1 + 4 * (2 * H2 + 1);
+
+__global__ void __launch_bounds__(TCD_THREADS) k_decoder_bwd_tc(const float* __restrict__ U, const float* __restrict__ V,
+                                                               const int64_t* __restrict__ pi, const int64_t* __restrict__ li,
+                                                               const float* __restrict__ W2, const float* __restrict__ b2,
+                                                               const float* __restrict__ w3, const float* __restrict__ dpred,
+                                                               const int32_t* __restrict__ ids, const int32_t* __restrict__ n_active_ptr,
+                                                               float p_drop, uint64_t seed, uint64_t sid1, uint64_t sid2,
+                                                               float* __restrict__ g_out, float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sb2[H2], sw3[H2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* base = dsm + ((1024u - (smem_u32(dsm) & 1023u)) & 1023u);
+  uint8_t* sZ = base;                          // [2][128 x 128 B]  z1           (A of MMA1)            32 KB
+  uint8_t* sA = base + 32768;                  // [1][128 x 128 B]  da2          (A of MMA2)            16 KB
+  uint8_t* sW = base + 49152;                  // [2][ 32 x 128 B]  W2   [n=32 rows][k=64]  (B of MMA1)   8 KB
+  uint8_t* sWT = base + 57344;                 // [1][ 64 x 128 B]  W2^T [n=64 rows][k=32]  (B of MMA2)   8 KB
+  for (int i = tid; i < H2 * (H1 / 4); i += TCD_THREADS) {
+    const int n = i / (H1 / 4), c16 = i % (H1 / 4);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W2 + n * H1) + c16);
+    *reinterpret_cast<float4*>(sW + (c16 >> 3) * 4096 + sw128(n, c16 & 7)) = w;
+    const float wv[4] = {w.x, w.y, w.z, w.w};      // transposed copy: element (j = n, k) -> row k, column j of W2^T
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = 4 * c16 + q;
+      *reinterpret_cast<float*>(sWT + sw128(k, n >> 2) + (n & 3) * 4) = wv[q];
+    }
   }
+  if (tid < H2) {
+    sb2[tid] = b2[tid];
+    sw3[tid] = w3[tid];
+  }
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  if (p_drop > 0.f) {
+    resolve_seed(seed, sid1);
+    sid2 &= ~SEED_IS_POINTER;
+  }
+  const int n_active = *n_active_ptr;
+  const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const uint32_t idesc1 = make_idesc(H2), idesc2 = make_idesc(H1);
+  const uint32_t za = smem_u32(sZ), aa = smem_u32(sA), wa = smem_u32(sW), wta = smem_u32(sWT);
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int oj = tid >> 2, okb = (tid & 3) * 16;      // this thread owns dW2[oj][okb .. okb+16)
+  float accW[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) accW[t] = 0.f;
+  float acc_b2 = 0.f, acc_w3 = 0.f, acc_b3 = 0.f;     // lane j of each warp holds column j
+  uint32_t phase = 0;
+
+  for (int t0 = blockIdx.x * TILE_M; t0 < n_active; t0 += gridDim.x * TILE_M) {
+    const int slot = t0 + tid;
+    const bool live = slot < n_active;
+    int64_t pair = 0;
+    float dy = 0.f;
+    unsigned long long zpos = 0ull;
+    {
+      float z[H1];
+      if (live) {
+        pair = ids[slot];
+        dy = dpred[pair];
+        load_z1(U, V, __ldg(pi + pair), __ldg(li + pair), p_drop, seed, sid1, pair, z);
+      } else {
+#pragma unroll
+        for (int k = 0; k < H1; ++k) z[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < H1; ++k) zpos |= (unsigned long long)(z[k] > 0.f) << k;
+#pragma unroll
+      for (int c16 = 0; c16 < H1 / 4; ++c16)
+        *reinterpret_cast<float4*>(sZ + (c16 >> 3) * 16384 + sw128(tid, c16 & 7)) =
+            make_float4(z[4 * c16], z[4 * c16 + 1], z[4 * c16 + 2], z[4 * c16 + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {                                    // MMA1: a2 = z1 W2^T
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8)
+          umma_tf32(tmem_base, make_desc(za + kb * 16384 + k8 * 32), make_desc(wa + kb * 4096 + k8 * 32), idesc1, (kb | k8) != 0);
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + lane_base, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float da[H2];
+#pragma unroll
+      for (int jg = 0; jg < H2 / 4; ++jg) {
+        float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p_drop > 0.f) mk = dropout_scale4(seed, sid2, (uint64_t)pair * (H2 / 4) + jg, p_drop);
+        const float mks[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = jg * 4 + q;
+          const float a = __uint_as_float(r[j]) + sb2[j];
+          const float z2d = fmaxf(a, 0.f) * mks[q];
+          const float d = (live && a > 0.f) ? dy * sw3[j] * mks[q] : 0.f;
+          da[j] = d;
+          const float s_b2 = warp_sum(d), s_w3 = warp_sum(live ? dy * z2d : 0.f);
+          if (lane == j) {
+            acc_b2 += s_b2;
+            acc_w3 += s_w3;
+          }
+        }
+      }
+      const float s3 = warp_sum(dy);
+      if (lane == 0) acc_b3 += s3;
+#pragma unroll
+      for (int c16 = 0; c16 < H2 / 4; ++c16)
+        *reinterpret_cast<float4*>(sA + sw128(tid, c16)) = make_float4(da[4 * c16], da[4 * c16 + 1], da[4 * c16 + 2], da[4 * c16 + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {                                    // MMA2: dz1 = da2 W2   (B = W2^T, K = 32)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int k8 = 0; k8 < 4; ++k8)
+        umma_tf32(tmem_base + 32, make_desc(aa + k8 * 32), make_desc(wta + k8 * 32), idesc2, k8 != 0);
+      umma_commit(&bar_mma);
+    }
+    // dW2 += da2^T z1 from the shared-memory tiles while the tensor core works on MMA2
+    const int n_tile = min(TILE_M, n_active - t0);
+#pragma unroll 2
+    for (int p = 0; p < n_tile; ++p) {
+      const float a = *reinterpret_cast<const float*>(sA + sw128(p, oj >> 2) + (oj & 3) * 4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = (okb >> 2) + q;
+        const float4 zv = *reinterpret_cast<const float4*>(sZ + (c >> 3) * 16384 + sw128(p, c & 7));
+        accW[4 * q + 0] = fmaf(a, zv.x, accW[4 * q + 0]);
+        accW[4 * q + 1] = fmaf(a, zv.y, accW[4 * q + 1]);
+        accW[4 * q + 2] = fmaf(a, zv.z, accW[4 * q + 2]);
+        accW[4 * q + 3] = fmaf(a, zv.w, accW[4 * q + 3]);
+      }
+    }
+    mbar_wait(&bar_mma, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      float4* grow = reinterpret_cast<float4*>(g_out + (size_t)pair * H1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + 32 + h * 32, r);      // warp-collective (.sync.aligned): every lane takes part
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const unsigned bits = (unsigned)(zpos >> (h * 32));
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o;
+            o.x = (bits >> (4 * q)) & 1u ? __uint_as_float(r[4 * q]) * keep_scale : 0.f;
+            o.y = (bits >> (4 * q + 1)) & 1u ? __uint_as_float(r[4 * q + 1]) * keep_scale : 0.f;
+            o.z = (bits >> (4 * q + 2)) & 1u ? __uint_as_float(r[4 * q + 2]) * keep_scale : 0.f;
+            o.w = (bits >> (4 * q + 3)) & 1u ? __uint_as_float(r[4 * q + 3]) * keep_scale : 0.f;
+            grow[h * 8 + q] = o;
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                   // next tile overwrites sZ / sA / TMEM
+  }
+  float* part = partial + (size_t)blockIdx.x * PART_TC;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) part[oj * H1 + okb + t] = accW[t];
+  float* pw = part + H2 * H1 + warp * (2 * H2 + 1);
+  pw[lane] = acc_b2;
+  pw[H2 + lane] = acc_w3;
+  if (lane == 0) pw[2 * H2] = acc_b3;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+  }
+}
+
+// out = sum over CTAs (and, for the bias-like sums, over the per-warp slots) of the partial records: one warp per output,
+// lanes stride over the records, fixed-order butterfly at the end (deterministic)
+__global__ void __launch_bounds__(256) k_decoder_bwd_final(const float* __restrict__ partial, int n_cta, int stride, int n_warps,
+                                                           float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dw3,
+                                                           float* __restrict__ db3) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= H2 * H1 + 2 * H2 + 1) return;
+  float s = 0.f;
+  if (i < H2 * H1) {
+    for (int c = lane; c < n_cta; c += 32) s += partial[(size_t)c * stride + i];
+  } else {
+    const int r = i - H2 * H1;  // 0..31 db2, 32..63 dw3, 64 db3
+    for (int q = lane; q < n_cta * n_warps; q += 32)
+      s += partial[(size_t)(q / n_warps) * stride + H2 * H1 + (q % n_warps) * (2 * H2 + 1) + r];
+  }
+  s = warp_sum(s);
+  if (lane != 0) return;
+  if (i < H2 * H1) dW2[i] = s;
+  else if (i < H2 * H1 + H2) db2[i - H2 * H1] = s;
+  else if (i < H2 * H1 + 2 * H2) dw3[i - H2 * H1 - H2] = s;
+  else db3[0] = s;
 }
 
 inline int bwd_ctas() { return 2 * sm_count(); }
@@ -355,12 +677,36 @@ extern "C" int b2g_decoder_fwd(const float* U, const float* V, const int64_t* pi
   return B2G_OK;
 }
 
-extern "C" size_t b2g_decoder_bwd_ws_bytes(int64_t m) {
-  size_t nb = (size_t)ceil_div(m > 0 ? m : 1, CMP_TILE);
-  return align_up((nb + 1) * 4, 256) * 2 + align_up((size_t)(m > 0 ? m : 1) * 4, 256) + align_up((size_t)bwd_ctas() * PART_STRIDE * 4, 256);
+/* tf32-mode forward: the 64 -> 32 layer on tcgen05 (TF32 operands, fp32 accumulate); same arguments and dropout streams */
+extern "C" int b2g_decoder_fwd_tc(const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2, const float* b2,
+                                  const float* w3, const float* b3, int64_t m, float p_drop, uint64_t seed, uint64_t sid1, uint64_t sid2,
+                                  float* pred, void* stream_) {
+  B2G_CHECK_ARG(m >= 0 && (m == 0 || (U && V && pi && li && W2 && b2 && w3 && b3 && pred)), "decoder_fwd_tc: null pointer");
+  B2G_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "decoder_fwd_tc: dropout p must be in [0,1)");
+  if (m == 0) return B2G_OK;
+  B2G_CHECK_ARG(aligned16(U) && aligned16(V) && aligned16(W2), "decoder_fwd_tc: U / V / W2 must be 16-byte aligned");
+  const size_t dyn = 2 * 16384 + 2 * 4096 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2G_CUDA(cudaFuncSetAttribute(k_decoder_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set = true;
+  }
+  int64_t tiles = ceil_div(m, TILE_M);
+  int64_t cap = (int64_t)sm_count() * 5;
+  int grid = (int)(tiles < cap ? tiles : cap);
+  k_decoder_fwd_tc<<<grid, TCD_THREADS, dyn, (cudaStream_t)stream_>>>(U, V, pi, li, W2, b2, w3, b3, m, p_drop, seed, sid1, sid2, pred);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
 }
 
-extern "C" int b2g_decoder_bwd(const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2, const float* b2,
+extern "C" size_t b2g_decoder_bwd_ws_bytes(int64_t m) {
+  size_t nb = (size_t)ceil_div(m > 0 ? m : 1, CMP_TILE);
+  size_t part = (size_t)bwd_ctas() * PART_STRIDE;
+  size_t part_tc = (size_t)3 * sm_count() * PART_TC;
+  return align_up((nb + 1) * 4, 256) * 2 + align_up((size_t)(m > 0 ? m : 1) * 4, 256) + align_up((part > part_tc ? part : part_tc) * 4, 256);
+}
+
+static int decoder_bwd_impl(bool use_tc, const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2, const float* b2,
                                const float* w3, const float* dpred, int64_t m, float p_drop, uint64_t seed, uint64_t sid1, uint64_t sid2,
                                float* g_rows, float* active_flags, float* dW2, float* db2, float* dw3, float* db3, void* ws,
                                size_t ws_bytes, void* stream_) {
@@ -388,6 +734,21 @@ extern "C" int b2g_decoder_bwd(const float* U, const float* V, const int64_t* pi
   B2G_LAUNCH_CHECK();
   k_compact_nonzero<<<nb, 256, 0, st>>>(dpred, m, block_off, ids, active_flags);
   B2G_LAUNCH_CHECK();
+  if (use_tc) {
+    static bool attr_tc = false;
+    const size_t dyn_tc = 65536 + 1024;
+    if (!attr_tc) {
+      B2G_CUDA(cudaFuncSetAttribute(k_decoder_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tc));
+      attr_tc = true;
+    }
+    const int ctas_tc = 3 * sm_count();
+    k_decoder_bwd_tc<<<ctas_tc, TCD_THREADS, dyn_tc, st>>>(U, V, pi, li, W2, b2, w3, dpred, ids, block_off + nb, p_drop, seed, sid1, sid2,
+                                                            g_rows, partial);
+    B2G_LAUNCH_CHECK();
+    k_decoder_bwd_final<<<(unsigned)ceil_div(H2 * H1 + 2 * H2 + 1, 8), 256, 0, st>>>(partial, ctas_tc, PART_TC, 4, dW2, db2, dw3, db3);
+    B2G_LAUNCH_CHECK();
+    return B2G_OK;
+  }
   static bool attr_set = false;
   const size_t dyn = (size_t)DEC_THREADS * (ZS + AS) * sizeof(float);
   if (!attr_set) {
@@ -398,7 +759,24 @@ extern "C" int b2g_decoder_bwd(const float* U, const float* V, const int64_t* pi
   k_decoder_bwd<<<ctas, DEC_THREADS, dyn, st>>>(U, V, pi, li, W2, b2, w3, dpred, ids, block_off + nb, p_drop, seed, sid1, sid2, g_rows,
                                                  partial);
   B2G_LAUNCH_CHECK();
-  k_decoder_bwd_final<<<(unsigned)ceil_div(H2 * H1 + 2 * H2 + 1, 256), 256, 0, st>>>(partial, ctas, dW2, db2, dw3, db3);
+  k_decoder_bwd_final<<<(unsigned)ceil_div(H2 * H1 + 2 * H2 + 1, 8), 256, 0, st>>>(partial, ctas, PART_STRIDE, 8, dW2, db2, dw3, db3);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
+}
+
+extern "C" int b2g_decoder_bwd(const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2, const float* b2,
+                               const float* w3, const float* dpred, int64_t m, float p_drop, uint64_t seed, uint64_t sid1, uint64_t sid2,
+                               float* g_rows, float* active_flags, float* dW2, float* db2, float* dw3, float* db3, void* ws,
+                               size_t ws_bytes, void* stream_) {
+  return decoder_bwd_impl(false, U, V, pi, li, W2, b2, w3, dpred, m, p_drop, seed, sid1, sid2, g_rows, active_flags, dW2, db2, dw3, db3, ws,
+                          ws_bytes, stream_);
+}
+
+/* tf32-mode backward: both per-pair contractions (a2 = z1 W2^T, dz1 = da2 W2) on tcgen05 */
+extern "C" int b2g_decoder_bwd_tc(const float* U, const float* V, const int64_t* pi, const int64_t* li, const float* W2, const float* b2,
+                                  const float* w3, const float* dpred, int64_t m, float p_drop, uint64_t seed, uint64_t sid1, uint64_t sid2,
+                                  float* g_rows, float* active_flags, float* dW2, float* db2, float* dw3, float* db3, void* ws,
+                                  size_t ws_bytes, void* stream_) {
+  return decoder_bwd_impl(true, U, V, pi, li, W2, b2, w3, dpred, m, p_drop, seed, sid1, sid2, g_rows, active_flags, dW2, db2, dw3, db3, ws,
+                          ws_bytes, stream_);
 }

@@ -265,12 +265,15 @@ __global__ void __launch_bounds__(256) k_wgrad_partial(const float* __restrict__
   }
 }
 
-__global__ void k_wgrad_reduce(const float* __restrict__ part, int slices, int64_t count, float* __restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// out[i] = sum over slices of part[slice][i]: one warp per output, lanes stride over the slices, fixed-order butterfly
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, int slices, int64_t count, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= count) return;
   float s = 0.f;
-  for (int sl = 0; sl < slices; ++sl) s += part[(size_t)sl * count + i];
-  out[i] = s;
+  for (int sl = lane; sl < slices; sl += 32) s += part[(size_t)sl * count + i];
+  s = warp_sum(s);
+  if (lane == 0) out[i] = s;
 }
 
 inline int wgrad_slices(int64_t m, int n, int k) {
@@ -354,10 +357,10 @@ extern "C" int b2g_linear_bwd_weight(const float* dy, const float* x, int64_t m,
   k_wgrad_partial<<<grid, 256, 0, st>>>(dy, x, m, n, k, rows, part_w, db ? part_b : nullptr);
   B2G_LAUNCH_CHECK();
   int64_t cnt = (int64_t)n * k;
-  k_wgrad_reduce<<<(unsigned)ceil_div(cnt, 256), 256, 0, st>>>(part_w, slices, cnt, dw);
+  k_wgrad_reduce<<<(unsigned)ceil_div(cnt, 8), 256, 0, st>>>(part_w, slices, cnt, dw);
   B2G_LAUNCH_CHECK();
   if (db) {
-    k_wgrad_reduce<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(part_b, slices, n, db);
+    k_wgrad_reduce<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(part_b, slices, n, db);
     B2G_LAUNCH_CHECK();
   }
   return B2G_OK;

@@ -13,100 +13,13 @@
 //            publishes the accumulator
 //   warp 2   TMEM allocator / deallocator
 //   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> + bias (+ previous Y when accumulating) -> 128-bit stores
-#include <cuda.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 using namespace b2g;
 
 constexpr int TC_THREADS = 256;
-constexpr int TILE_M = 128;
-constexpr int KB = 32;                          // floats per 128-byte swizzle row
 constexpr int SUB_BYTES = TILE_M * KB * 4;      // one [128 rows x 128 B] sub-tile of X = 16 KB
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n"
-      ".reg .b32 rx;\n"
-      ".reg .pred px;\n"
-      "elect.sync rx|px, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, px;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
-// LBO (unused for swizzled K-major) in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48),
-// layout type SWIZZLE_128B (= 2) in [61,64).  The tile base must be 1024-byte aligned (base_offset = 0).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// cute::UMMA::InstrDescriptor for kind::tf32: c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10)/[10,13), K-major A and B
-// (bits 15,16 = 0), N >> 3 in [17,23), M >> 4 in [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
 
 struct TcParams {
   const float* bias;   // [N] or null
@@ -361,11 +274,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tf32(const __grid_const
 }
 
 // out[i] = sum over CTAs of partial[c][i] (fixed order); optionally transposed: partial is [128][nb] = dW^T
-__global__ void k_wgrad_tc_reduce(const float* __restrict__ partial, int n_cta, int rows, int cols, int transpose, float* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_wgrad_tc_reduce(const float* __restrict__ partial, int n_cta, int rows, int cols, int transpose,
+                                                         float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);      // one warp per output element, lanes stride over the CTAs
   if (i >= rows * cols) return;
   float s = 0.f;
-  for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * rows * cols + i];
+  for (int c = lane; c < n_cta; c += 32) s += partial[(size_t)c * rows * cols + i];
+  s = warp_sum(s);
+  if (lane != 0) return;
   if (transpose) {
     int r = i / cols, cc = i % cols;
     out[(size_t)cc * rows + r] = s;
@@ -529,7 +446,7 @@ extern "C" int b2g_linear_bwd_weight_tc(const float* dy, const float* x, int64_t
   k_wgrad_tf32<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, prm);
   B2G_LAUNCH_CHECK();
   // partial[c] is [128][nb]: equals dW[N,K] when !swap (rows = n), dW^T when swap (rows = k, cols = n)
-  k_wgrad_tc_reduce<<<(unsigned)ceil_div(128 * nb, 256), 256, 0, st>>>(prm.partial, grid, 128, nb, swap ? 1 : 0, dw);
+  k_wgrad_tc_reduce<<<(unsigned)ceil_div(128 * nb, 8), 256, 0, st>>>(prm.partial, grid, 128, nb, swap ? 1 : 0, dw);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

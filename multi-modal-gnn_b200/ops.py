@@ -605,9 +605,10 @@ class DecoderHeadFn(Function):
         p = float(p_drop) if training else 0.0
         pred = torch.empty(pairs.m, dtype=torch.float32, device=u.device)
         cost(pairs.m * (16 + 4 + 256) + 4 * v.numel(), 2 * pairs.m * (64 * 32 + 32 + 64))
-        _run("b2g_decoder_fwd", lib.b2g_decoder_fwd, u.data_ptr(), v.data_ptr(), pairs.patient_idx.data_ptr(), pairs.lab_idx.data_ptr(),
-             w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), pairs.m, p, int(seed), int(sid1), int(sid2), pred.data_ptr(),
-             _stream())
+        tc = PRECISION == "tf32" and pairs.m >= TC_MIN_ROWS
+        _run("b2g_decoder_fwd_tc" if tc else "b2g_decoder_fwd", lib.b2g_decoder_fwd_tc if tc else lib.b2g_decoder_fwd, u.data_ptr(),
+             v.data_ptr(), pairs.patient_idx.data_ptr(), pairs.lab_idx.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(),
+             b3.data_ptr(), pairs.m, p, int(seed), int(sid1), int(sid2), pred.data_ptr(), _stream())
         ctx.save_for_backward(u, v, w2, b2, w3)
         ctx.meta = (pairs, p, int(seed), int(sid1), int(sid2))
         return pred
@@ -629,7 +630,9 @@ class DecoderHeadFn(Function):
         db3 = torch.empty(1, dtype=torch.float32, device=dev)
         ws = workspace(lib.b2g_decoder_bwd_ws_bytes(m), dev)
         cost(m * (16 + 4 + 4) + m // 5 * 512, 2 * (m // 5) * 3 * 64 * 32)
-        _run("b2g_decoder_bwd", lib.b2g_decoder_bwd, u.data_ptr(), v.data_ptr(), pairs.patient_idx.data_ptr(), pairs.lab_idx.data_ptr(),
+        tc = PRECISION == "tf32" and m >= TC_MIN_ROWS
+        _run("b2g_decoder_bwd_tc" if tc else "b2g_decoder_bwd", lib.b2g_decoder_bwd_tc if tc else lib.b2g_decoder_bwd, u.data_ptr(),
+             v.data_ptr(), pairs.patient_idx.data_ptr(), pairs.lab_idx.data_ptr(),
              w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), dpred.data_ptr(), m, p, seed, sid1, sid2, g.data_ptr(), flags.data_ptr(),
              dw2.data_ptr(), db2.data_ptr(), dw3.data_ptr(), db3.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
         du = dv = None

@@ -741,3 +741,73 @@ def test_cuda_graph_step_equals_eager_step(dev):
         td.model._seed_buffer.fill_(12345)
         c = td.model.predict_lab_values(td.data, pi, li)
     assert not torch.equal(a, b) and torch.equal(b, c)
+
+
+@pytest.mark.parametrize("m,p_drop", [(512, 0.0), (1000, 0.0), (43038, 0.2), (300000, 0.2)])
+def test_fused_decoder_tensor_core_forward(m, p_drop, dev):
+    """tf32 mode: k_decoder_fwd_tc (thread-written swizzled A tile + tcgen05) against the exact-fp32 SIMT kernel with
+    the same dropout streams."""
+    pkg, G, ops, M, T, L = _mods()
+    lib = L.load()
+    gen = torch.Generator().manual_seed(m)
+    n_p, n_l = 5000, 160
+    U, V = torch.randn(n_p, 64, generator=gen).to(dev), torch.randn(n_l, 64, generator=gen).to(dev)
+    pi, li = torch.randint(0, n_p, (m,), generator=gen).to(dev), torch.randint(0, n_l, (m,), generator=gen).to(dev)
+    W2, b2 = (torch.randn(32, 64, generator=gen) / 8).to(dev), torch.randn(32, generator=gen).to(dev)
+    w3, b3 = torch.randn(32, generator=gen).to(dev), torch.randn(1, generator=gen).to(dev)
+    ref, out = torch.empty(m, device=dev), torch.full((m,), float("nan"), device=dev)
+    args = (U.data_ptr(), V.data_ptr(), pi.data_ptr(), li.data_ptr(), W2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), m, p_drop,
+            777, 3, 4)
+    L.check(lib.b2g_decoder_fwd(*args, ref.data_ptr(), None))
+    L.check(lib.b2g_decoder_fwd_tc(*args, out.data_ptr(), None))
+    assert relerr(out, ref) <= 3e-3
+    out2 = torch.empty(m, device=dev)
+    L.check(lib.b2g_decoder_fwd_tc(*args, out2.data_ptr(), None))
+    assert torch.equal(out, out2)
+    # TF32-representable operands -> equal up to accumulation order
+    Uq, Vq = (torch.randint(-8, 9, (n_p, 64), generator=gen).float() / 16).to(dev), (torch.randint(-8, 9, (n_l, 64), generator=gen).float() / 16).to(dev)
+    W2q = (torch.randint(-8, 9, (32, 64), generator=gen).float() / 8).to(dev)
+    argsq = (Uq.data_ptr(), Vq.data_ptr(), pi.data_ptr(), li.data_ptr(), W2q.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), m, 0.0, 0, 0, 0)
+    L.check(lib.b2g_decoder_fwd(*argsq, ref.data_ptr(), None))
+    L.check(lib.b2g_decoder_fwd_tc(*argsq, out.data_ptr(), None))
+    assert relerr(out, ref) <= 2e-6
+
+
+@pytest.mark.parametrize("m,p_drop,frac", [(600, 0.0, 1.0), (43038, 0.2, 0.2), (300000, 0.2, 0.2), (5000, 0.0, 0.0)])
+def test_fused_decoder_tensor_core_backward(m, p_drop, frac, dev):
+    """tf32 mode: k_decoder_bwd_tc against the exact-fp32 SIMT backward (same dropout streams, same compaction)."""
+    pkg, G, ops, M, T, L = _mods()
+    lib = L.load()
+    gen = torch.Generator().manual_seed(m + 1)
+    n_p, n_l = 5000, 160
+    U, V = torch.randn(n_p, 64, generator=gen).to(dev), torch.randn(n_l, 64, generator=gen).to(dev)
+    pi, li = torch.randint(0, n_p, (m,), generator=gen).to(dev), torch.randint(0, n_l, (m,), generator=gen).to(dev)
+    W2, b2 = (torch.randn(32, 64, generator=gen) / 8).to(dev), torch.randn(32, generator=gen).to(dev)
+    w3 = torch.randn(32, generator=gen).to(dev)
+    dpred = (torch.randn(m, generator=gen) * (torch.rand(m, generator=gen) < frac)).to(dev)
+    ws = torch.empty(lib.b2g_decoder_bwd_ws_bytes(m), dtype=torch.uint8, device=dev)
+
+    def run(fn):
+        g = torch.zeros(m, 64, device=dev)
+        flags = torch.empty(m, device=dev)
+        dW2, db2, dw3, db3 = torch.empty(32, 64, device=dev), torch.empty(32, device=dev), torch.empty(32, device=dev), torch.empty(1, device=dev)
+        L.check(fn(U.data_ptr(), V.data_ptr(), pi.data_ptr(), li.data_ptr(), W2.data_ptr(), b2.data_ptr(), w3.data_ptr(), dpred.data_ptr(), m,
+                   p_drop, 99, 1, 2, g.data_ptr(), flags.data_ptr(), dW2.data_ptr(), db2.data_ptr(), dw3.data_ptr(), db3.data_ptr(),
+                   ws.data_ptr(), ws.numel(), None))
+        torch.cuda.synchronize()
+        return g * flags.unsqueeze(1), flags, dW2, db2, dw3, db3
+
+    ref, out = run(lib.b2g_decoder_bwd), run(lib.b2g_decoder_bwd_tc)
+    assert torch.equal(ref[1], out[1]) and torch.equal(ref[1], (dpred != 0).float())
+    if frac == 0.0:
+        for a in out[2:]:
+            assert float(a.abs().max()) == 0.0
+        return
+    # TF32 can flip the sign of a near-zero layer-2 pre-activation, which toggles that unit's ReLU derivative for the
+    # pair: a few rows differ visibly by construction, so compare in norm and bound the fraction of such rows
+    for name, a, b in zip(("g", "dW2", "db2", "dw3", "db3"), (out[0], *out[2:]), (ref[0], *ref[2:])):
+        assert float((a - b).norm() / b.norm().clamp_min(1e-30)) <= 2e-2, name
+    row_err = (out[0] - ref[0]).abs().max(1)[0]
+    assert float((row_err > 5e-3 * ref[0].abs().max()).float().mean()) <= 0.02
+    out2 = run(lib.b2g_decoder_bwd_tc)
+    assert torch.equal(out[0], out2[0]) and torch.equal(out[2], out2[2])
