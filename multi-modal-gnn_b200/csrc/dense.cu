@@ -131,52 +131,53 @@ template <bool A_T, bool B_NK>
 __global__ void __launch_bounds__(256) k_sgemm_small(const float* __restrict__ Ap, const float* __restrict__ Bp,
                                                      const float* __restrict__ bias, int M, int N, int K, float* __restrict__ C,
                                                      int accumulate) {
-  __shared__ float As[32][33];   // [k][m]
-  __shared__ float Bs[32][33];   // [k][n]
+  constexpr int KT = 128;          // the whole reduction of a d = 128 layer in ONE load phase: these launches are latency-bound
+  __shared__ float As[KT][33];     // [k][m]
+  __shared__ float Bs[KT][33];     // [k][n]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
-  const int lr = tid >> 3, lq = (tid & 7) * 4;     // loader coordinates: row 0..31, 4 consecutive elements
+  const int lr = tid >> 3, lq = (tid & 7) * 4;     // loader coordinates: row 0..31, 4 consecutive elements (+ 32 * j)
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  float ra[4], rb[4];
-  auto load = [&](int k0) {
+  for (int k0 = 0; k0 < K; k0 += KT) {
+    float ra[16], rb[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (A_T) {          // row = k, consecutive m
-        int k = k0 + lr, m = m0 + lq + q;
-        ra[q] = (k < K && m < M) ? __ldg(Ap + (size_t)k * M + m) : 0.f;
-      } else {            // row = m, consecutive k
-        int m = m0 + lr, k = k0 + lq + q;
-        ra[q] = (m < M && k < K) ? __ldg(Ap + (size_t)m * K + k) : 0.f;
-      }
-      if (B_NK) {         // row = n, consecutive k
-        int n = n0 + lr, k = k0 + lq + q;
-        rb[q] = (n < N && k < K) ? __ldg(Bp + (size_t)n * K + k) : 0.f;
-      } else {            // row = k, consecutive n
-        int k = k0 + lr, n = n0 + lq + q;
-        rb[q] = (k < K && n < N) ? __ldg(Bp + (size_t)k * N + n) : 0.f;
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (A_T) {          // A stored [K, M]: row = k, consecutive m
+          int k = k0 + lr + 32 * j, m = m0 + lq + q;
+          ra[4 * j + q] = (k < K && m < M) ? __ldg(Ap + (size_t)k * M + m) : 0.f;
+        } else {            // A stored [M, K]: row = m, consecutive k
+          int m = m0 + lr, k = k0 + lq + q + 32 * j;
+          ra[4 * j + q] = (m < M && k < K) ? __ldg(Ap + (size_t)m * K + k) : 0.f;
+        }
+        if (B_NK) {         // B stored [N, K]: row = n, consecutive k
+          int n = n0 + lr, k = k0 + lq + q + 32 * j;
+          rb[4 * j + q] = (n < N && k < K) ? __ldg(Bp + (size_t)n * K + k) : 0.f;
+        } else {            // B stored [K, N]: row = k, consecutive n
+          int k = k0 + lr + 32 * j, n = n0 + lq + q;
+          rb[4 * j + q] = (k < K && n < N) ? __ldg(Bp + (size_t)k * N + n) : 0.f;
+        }
       }
     }
-  };
-  auto stash = [&]() {
+    __syncthreads();       // previous chunk fully consumed
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (A_T) As[lr][lq + q] = ra[q]; else As[lq + q][lr] = ra[q];
-      if (B_NK) Bs[lq + q][lr] = rb[q]; else Bs[lr][lq + q] = rb[q];
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (A_T) As[lr + 32 * j][lq + q] = ra[4 * j + q]; else As[lq + q + 32 * j][lr] = ra[4 * j + q];
+        if (B_NK) Bs[lq + q + 32 * j][lr] = rb[4 * j + q]; else Bs[lr + 32 * j][lq + q] = rb[4 * j + q];
+      }
     }
-  };
-  load(0);
-  for (int k0 = 0; k0 < K; k0 += 32) {
-    stash();
     __syncthreads();
-    if (k0 + 32 < K) load(k0 + 32);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
+    const int kmax = min(KT, K - k0);
+#pragma unroll 8
+    for (int k = 0; k < kmax; ++k) {
       float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
       float b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
       acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
       acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
