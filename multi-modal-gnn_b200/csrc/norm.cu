@@ -2,12 +2,14 @@
 // Reference ops: nn.BatchNorm1d / F.relu / F.dropout / F.normalize (model.py:93-105,134-139,259-269),
 // weighted MAE/MSE (train.py:364-386), compute_regression_loss (model.py:579-612).
 // All reductions are two-stage and order-fixed (deterministic); column statistics accumulate in fp64.
+#include <atomic>
 #include "common.cuh"
 
 namespace {
 using namespace b2g;
 
-constexpr int MAX_PARTIALS = 296;  // 2 x 148 CTAs
+constexpr int MAX_PARTIALS = 296;  // upper bound on the CTAs of a column reduction (workspace sizing)
+constexpr int COL_THREADS = 512;
 
 // activation codes (model.py:145-153): 0 none, 1 relu, 2 leaky_relu(0.01), 3 elu(alpha 1)
 __device__ __forceinline__ float act_fwd(float v, int act) {
@@ -23,141 +25,151 @@ __device__ __forceinline__ float act_grad(float pre, int act) {
   return 1.f;
 }
 
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 // ---- column reductions ------------------------------------------------------------------------------------------
-// MODE 0: s0 = sum x,        s1 = sum x^2                    (batch statistics)
-// MODE 1: s0 = sum g,        s1 = sum g * xhat                (BN backward), g = dy * dropmask * relu'
+// One kernel per reduction: every CTA reduces its rows to a per-CTA fp64 partial (fixed order), takes a ticket, and the
+// CTA that draws the last ticket adds the partials in CTA order and applies the finalisation (so the result does not
+// depend on which CTA finishes last: deterministic), all in the same launch.
+//   MODE 0: s0 = sum x,        s1 = sum x^2                    (batch statistics, column sums)
+//   MODE 1: s0 = sum g,        s1 = sum g * xhat                (BN backward), g = dy * dropmask * act'
+//   FIN  0: mean / rstd (+ running-stat update like nn.BatchNorm1d in training mode)
+//        1: sums[2d] (double) + dbeta / dgamma     2: out[c] = (float)s0     3: sums[2d] (double) only
+struct ColFin {
+  int kind;
+  int64_t m;
+  float eps, momentum;
+  float *mean, *rstd, *running_mean, *running_var;   // kind 0
+  double* sums;                                       // kind 1, 3
+  float *dgamma, *dbeta;                              // kind 1
+  float* out;                                         // kind 2
+};
+
+__device__ unsigned int g_tickets[1024];   // zero at load; the last CTA of a launch resets its slot.  Slots rotate per launch
+                                           // (host counter), so concurrent streams collide only 1024 launches apart.
+
 template <int MODE>
-__global__ void __launch_bounds__(256) k_col_partial(const float* __restrict__ x, const float* __restrict__ dy, int64_t m, int d,
-                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                     const float* __restrict__ gamma, const float* __restrict__ beta, int relu, float p_drop,
-                                                     uint64_t seed, uint64_t sid, double* __restrict__ partial) {
+__global__ void __launch_bounds__(COL_THREADS) k_col_reduce(const float* __restrict__ x, const float* __restrict__ dy, int64_t m, int d,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                                            float p_drop, uint64_t seed, uint64_t sid, double* __restrict__ partial,
+                                                            int ticket_slot, ColFin fin) {
   extern __shared__ double sm[];  // [rows_per_pass][2][d]
+  __shared__ int is_last;
   if (MODE == 1 && p_drop > 0.f) resolve_seed(seed, sid);
-  const int tpr = d >> 2;               // threads per row (float4 each)
-  const int rpp = 256 / tpr;            // rows per pass of the block
+  const int tpr = d >> 3;               // threads per row (8 columns each = one Philox call)
+  const int rpp = COL_THREADS / tpr;    // rows per pass of the block
   const int cg = threadIdx.x % tpr, rs = threadIdx.x / tpr;
-  const int c = cg * 4;
-  double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
-  float mu[4] = {0, 0, 0, 0}, rsd[4] = {1, 1, 1, 1}, ga[4] = {1, 1, 1, 1}, be[4] = {0, 0, 0, 0};
-  if (MODE == 1) {
+  const int c = cg * 8;
+  double a0[8], a1[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      mu[q] = mean[c + q]; rsd[q] = rstd[c + q]; ga[q] = gamma[c + q]; be[q] = beta[c + q];
-    }
+  for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.0;
+  float mu[8], rsd[8], ga[8], be[8];
+  if (MODE == 1) {
+    ld8(mean + c, mu); ld8(rstd + c, rsd); ld8(gamma + c, ga); ld8(beta + c, be);
   }
+#pragma unroll 2
   for (int64_t r = (int64_t)blockIdx.x * rpp + rs; r < m; r += (int64_t)gridDim.x * rpp) {
     const size_t off = (size_t)r * d + c;
-    float4 xv = ld_stream(reinterpret_cast<const float4*>(x + off));
-    float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    float xs[8];
+    ld8(x + off, xs);
     if (MODE == 0) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        a0[q] += (double)xs[q];
-        a1[q] += (double)xs[q] * (double)xs[q];
+      for (int e = 0; e < 8; ++e) {
+        a0[e] += (double)xs[e];
+        a1[e] += (double)xs[e] * (double)xs[e];
       }
     } else {
-      float4 gv = ld_stream(reinterpret_cast<const float4*>(dy + off));
-      float g[4] = {gv.x, gv.y, gv.z, gv.w};
+      float g[8];
+      ld8(dy + off, g);
       if (p_drop > 0.f) {
-        float4 mk = dropout_scale4(seed, sid, off >> 2, p_drop);
-        g[0] *= mk.x; g[1] *= mk.y; g[2] *= mk.z; g[3] *= mk.w;
+        float mk[8];
+        dropout_scale8(seed, sid, off >> 3, p_drop, mk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] *= mk[e];
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float xh = (xs[q] - mu[q]) * rsd[q];
-        g[q] *= act_grad(fmaf(xh, ga[q], be[q]), relu);
-        a0[q] += (double)g[q];
-        a1[q] += (double)g[q] * (double)xh;
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xs[e] - mu[e]) * rsd[e];
+        g[e] *= act_grad(fmaf(xh, ga[e], be[e]), act);
+        a0[e] += (double)g[e];
+        a1[e] += (double)g[e] * (double)xh;
       }
     }
   }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    sm[(size_t)(rs * 2 + 0) * d + c + q] = a0[q];
-    sm[(size_t)(rs * 2 + 1) * d + c + q] = a1[q];
+  for (int e = 0; e < 8; ++e) {
+    sm[(size_t)(rs * 2 + 0) * d + c + e] = a0[e];
+    sm[(size_t)(rs * 2 + 1) * d + c + e] = a1[e];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * d; i += 256) {
-    int which = i / d, col = i % d;
+  for (int i = threadIdx.x; i < 2 * d; i += COL_THREADS) {
+    const int which = i / d, col = i % d;
     double s = 0;
     for (int rr = 0; rr < rpp; ++rr) s += sm[(size_t)(rr * 2 + which) * d + col];
     partial[((size_t)blockIdx.x * 2 + which) * d + col] = s;
   }
-}
-
-// deterministic column totals of the per-CTA partials: 32 columns x 8 slices per block, slices combined in fixed order
-__device__ __forceinline__ void reduce_partials(const double* __restrict__ partial, int n_part, int d, int c, int slice, double& s0,
-                                                double& s1) {
-  __shared__ double sh[2][8][32];
-  double a0 = 0, a1 = 0;
-  if (c < d) {
-    for (int p = slice; p < n_part; p += 8) {
-      a0 += partial[((size_t)p * 2 + 0) * d + c];
-      a1 += partial[((size_t)p * 2 + 1) * d + c];
-    }
-  }
-  sh[0][slice][threadIdx.x & 31] = a0;
-  sh[1][slice][threadIdx.x & 31] = a1;
+  // ---- ticket: the last CTA finalises ----
+  __threadfence();
   __syncthreads();
-  s0 = s1 = 0;
-  if (slice == 0) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s0 += sh[0][k][threadIdx.x & 31];
-      s1 += sh[1][k][threadIdx.x & 31];
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&g_tickets[ticket_slot], 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int n_part = gridDim.x, outs = 2 * d;
+  const int n_slices = COL_THREADS / outs > 0 ? COL_THREADS / outs : 1;   // d = 256: 1, 128: 2, 64: 4, 32: 8
+  double* comb = sm;                                                        // [n_slices][outs]
+  for (int o0 = 0; o0 < outs; o0 += COL_THREADS) {
+    const int idx = o0 + threadIdx.x;
+    const int o = idx % outs, sl = (idx / outs) % n_slices;
+    if (idx < outs * n_slices) {
+      double acc = 0;
+#pragma unroll 8
+      for (int p = sl; p < n_part; p += n_slices) acc += __ldcg(partial + (size_t)p * outs + o);
+      comb[sl * outs + o] = acc;
     }
   }
-}
-
-// stage 2 of MODE 0: mean / rstd (+ running-stat update like nn.BatchNorm1d in training mode); block = 256 threads
-__global__ void __launch_bounds__(256) k_bn_finalize(const double* __restrict__ partial, int n_part, int64_t m, int d, float eps, float momentum,
-                                                     float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
-                                                     float* __restrict__ running_var) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
-  double s0, s1;
-  reduce_partials(partial, n_part, d, c, slice, s0, s1);
-  if (slice != 0 || c >= d) return;
-  double mu = s0 / (double)m;
-  double var = s1 / (double)m - mu * mu;
-  if (var < 0) var = 0;
-  mean[c] = (float)mu;
-  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
-  if (running_var) {
-    double unb = m > 1 ? var * ((double)m / (double)(m - 1)) : var;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < d; cc += COL_THREADS) {
+    double s0 = 0, s1 = 0;
+    for (int sl = 0; sl < n_slices; ++sl) {
+      s0 += comb[sl * outs + cc];
+      s1 += comb[sl * outs + d + cc];
+    }
+    if (fin.kind == 0) {
+      const double mm = (double)fin.m;
+      const double mean_ = s0 / mm;
+      double var = s1 / mm - mean_ * mean_;
+      if (var < 0) var = 0;
+      fin.mean[cc] = (float)mean_;
+      fin.rstd[cc] = (float)(1.0 / sqrt(var + (double)fin.eps));
+      if (fin.running_mean) fin.running_mean[cc] = (1.f - fin.momentum) * fin.running_mean[cc] + fin.momentum * (float)mean_;
+      if (fin.running_var) {
+        const double unb = fin.m > 1 ? var * (mm / (double)(fin.m - 1)) : var;
+        fin.running_var[cc] = (1.f - fin.momentum) * fin.running_var[cc] + fin.momentum * (float)unb;
+      }
+    } else if (fin.kind == 1 || fin.kind == 3) {
+      fin.sums[cc] = s0;
+      fin.sums[d + cc] = s1;
+      if (fin.kind == 1) {
+        if (fin.dbeta) fin.dbeta[cc] = (float)s0;
+        if (fin.dgamma) fin.dgamma[cc] = (float)s1;
+      }
+    } else {
+      fin.out[cc] = (float)s0;
+    }
   }
-}
-
-// stage 2 of MODE 1: totals -> sums[2][d] (double) and dbeta / dgamma
-__global__ void __launch_bounds__(256) k_bn_bwd_finalize(const double* __restrict__ partial, int n_part, int d, double* __restrict__ sums,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
-  double s0, s1;
-  reduce_partials(partial, n_part, d, c, slice, s0, s1);
-  if (slice != 0 || c >= d) return;
-  sums[c] = s0;
-  sums[d + c] = s1;
-  if (dbeta) dbeta[c] = (float)s0;
-  if (dgamma) dgamma[c] = (float)s1;
-}
-
-__global__ void __launch_bounds__(256) k_colsum_finalize(const double* __restrict__ partial, int n_part, int d, float* __restrict__ out) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
-  double s0, s1;
-  reduce_partials(partial, n_part, d, c, slice, s0, s1);
-  if (slice == 0 && c < d) out[c] = (float)s0;
-}
-
-
-// ---- split statistics for patient-partitioned (multi-GPU) BatchNorm: local totals -> all-reduce -> finalize ----------------
-__global__ void __launch_bounds__(256) k_col_totals(const double* __restrict__ partial, int n_part, int d, double* __restrict__ sums) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
-  double s0, s1;
-  reduce_partials(partial, n_part, d, c, slice, s0, s1);
-  if (slice != 0 || c >= d) return;
-  sums[c] = s0;
-  sums[d + c] = s1;
+  if (threadIdx.x == 0) g_tickets[ticket_slot] = 0u;
 }
 
 __global__ void k_bn_finalize_sums(const double* __restrict__ sums, double m, int d, float eps, float momentum, float* __restrict__ mean,
@@ -191,60 +203,63 @@ __global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __res
   rstd[c] = 1.0f / sqrtf(rv[c] + eps);
 }
 
-__global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ x, int64_t n4, int d, const float* __restrict__ mean,
+// Element-wise passes: a thread owns 8 consecutive elements (one Philox call, two 16-byte accesses).  256 threads x 8
+// elements is a multiple of every supported d, so a thread's columns -- and its 8 x 4 parameters -- never change over the
+// grid-stride loop.
+__global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ x, int64_t n8, int d, const float* __restrict__ mean,
                                                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                  int relu, float p_drop, uint64_t seed, uint64_t sid, float* __restrict__ y) {
+                                                  int act, float p_drop, uint64_t seed, uint64_t sid, float* __restrict__ y) {
   if (p_drop > 0.f) resolve_seed(seed, sid);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)((i * 4) % d);
-    float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + i);
-    float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
-    float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
-    float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
-    float4 o;
-    o.x = fmaf((xv.x - mu.x) * rs.x, ga.x, be.x);
-    o.y = fmaf((xv.y - mu.y) * rs.y, ga.y, be.y);
-    o.z = fmaf((xv.z - mu.z) * rs.z, ga.z, be.z);
-    o.w = fmaf((xv.w - mu.w) * rs.w, ga.w, be.w);
-    o.x = act_fwd(o.x, relu); o.y = act_fwd(o.y, relu); o.z = act_fwd(o.z, relu); o.w = act_fwd(o.w, relu);
+  const int c = (int)((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8) % d);
+  float mu[8], rs[8], ga[8], be[8];
+  ld8(mean + c, mu); ld8(rstd + c, rs); ld8(gamma + c, ga); ld8(beta + c, be);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    ld8(x + i * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = act_fwd(fmaf((v[e] - mu[e]) * rs[e], ga[e], be[e]), act);
     if (p_drop > 0.f) {
-      float4 mk = dropout_scale4(seed, sid, (uint64_t)i, p_drop);
-      o.x *= mk.x; o.y *= mk.y; o.z *= mk.z; o.w *= mk.w;
+      float mk[8];
+      dropout_scale8(seed, sid, (uint64_t)i, p_drop, mk);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= mk[e];
     }
-    reinterpret_cast<float4*>(y)[i] = o;
+    st8(y + i * 8, v);
   }
 }
 
-__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, int64_t n4, int64_t m, int d,
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, int64_t n8, int64_t m, int d,
                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                      const float* __restrict__ gamma, const float* __restrict__ beta, int relu, float p_drop,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta, int act, float p_drop,
                                                       uint64_t seed, uint64_t sid, int batch_stats, const double* __restrict__ sums,
                                                       float* __restrict__ dx) {
   if (p_drop > 0.f) resolve_seed(seed, sid);
   const float inv_m = 1.0f / (float)m;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)((i * 4) % d);
-    float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + i);
-    float4 gv = ld_stream(reinterpret_cast<const float4*>(dy) + i);
-    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, g[4] = {gv.x, gv.y, gv.z, gv.w}, o[4];
+  const int c = (int)((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8) % d);
+  float mu[8], rs[8], ga[8], be[8], sg[8], sgx[8];
+  ld8(mean + c, mu); ld8(rstd + c, rs); ld8(gamma + c, ga); ld8(beta + c, be);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sg[e] = batch_stats ? (float)sums[c + e] * inv_m : 0.f;
+    sgx[e] = batch_stats ? (float)sums[d + c + e] * inv_m : 0.f;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float xs[8], g[8];
+    ld8(x + i * 8, xs);
+    ld8(dy + i * 8, g);
     if (p_drop > 0.f) {
-      float4 mk = dropout_scale4(seed, sid, (uint64_t)i, p_drop);
-      g[0] *= mk.x; g[1] *= mk.y; g[2] *= mk.z; g[3] *= mk.w;
+      float mk[8];
+      dropout_scale8(seed, sid, (uint64_t)i, p_drop, mk);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] *= mk[e];
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float mu = __ldg(mean + c + q), rs = __ldg(rstd + c + q), ga = __ldg(gamma + c + q), be = __ldg(beta + c + q);
-      float xh = (xs[q] - mu) * rs;
-      g[q] *= act_grad(fmaf(xh, ga, be), relu);
-      if (batch_stats) {
-        float sg = (float)sums[c + q] * inv_m, sgx = (float)sums[d + c + q] * inv_m;
-        o[q] = ga * rs * (g[q] - sg - xh * sgx);
-      } else {
-        o[q] = ga * rs * g[q];
-      }
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (xs[e] - mu[e]) * rs[e];
+      g[e] *= act_grad(fmaf(xh, ga[e], be[e]), act);
+      g[e] = batch_stats ? ga[e] * rs[e] * (g[e] - sg[e] - xh * sgx[e]) : ga[e] * rs[e] * g[e];
     }
-    reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    st8(dx + i * 8, g);
   }
 }
 
@@ -422,71 +437,70 @@ inline int ew_grid(int64_t n_items) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 inline int col_parts(int64_t m, int d) {
-  int rpp = 256 / (d / 4);
-  int64_t g = ceil_div(m, (int64_t)rpp * 8);
-  return (int)(g < 1 ? 1 : (g > MAX_PARTIALS ? MAX_PARTIALS : g));
+  int rpp = COL_THREADS / (d / 8);
+  int64_t g = ceil_div(m, (int64_t)rpp * 4);          // >= 4 passes per CTA before another CTA is worth its partial
+  int cap = sm_count() < MAX_PARTIALS ? sm_count() : MAX_PARTIALS;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+inline size_t col_smem(int d) { return (size_t)(COL_THREADS / (d / 8)) * 2 * d * sizeof(double); }
+inline int next_ticket_slot() {
+  static std::atomic<unsigned> n{0};
+  return (int)(n.fetch_add(1u) & 1023u);
+}
+template <int MODE>
+int launch_col_reduce(const float* x, const float* dy, int64_t m, int d, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, int act, float p_drop, uint64_t seed, uint64_t sid, double* partial, const ColFin& fin,
+                      cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2G_CUDA(cudaFuncSetAttribute(k_col_reduce<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    attr_set = true;
+  }
+  k_col_reduce<MODE><<<col_parts(m, d), COL_THREADS, col_smem(d), st>>>(x, dy, m, d, mean, rstd, gamma, beta, act, p_drop, seed, sid, partial,
+                                                                        next_ticket_slot(), fin);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
 }
 inline bool d_ok(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 }  // namespace
 
 extern "C" size_t b2g_bn_ws_bytes(int d) { return align_up((size_t)MAX_PARTIALS * 2 * d * 8, 256) + align_up((size_t)2 * d * 8, 256); }
 
+#define COL_WS_CHECK(name)                                   \
+  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {                \
+    set_error(name ": workspace too small");                 \
+    return B2G_EWS;                                          \
+  }
+
 extern "C" int b2g_bn_stats(const float* x, int64_t m, int d, float eps, float momentum, float* mean, float* rstd, float* running_mean,
                             float* running_var, void* ws, size_t ws_bytes, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(x && mean && rstd && m > 0 && d_ok(d) && aligned16(x), "bn_stats: bad args (m=%lld d=%d)", (long long)m, d);
-  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
-    set_error("bn_stats: workspace too small");
-    return B2G_EWS;
-  }
-  double* partial = (double*)ws;
-  int parts = col_parts(m, d);
-  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
-  k_col_partial<0><<<parts, 256, smem, st>>>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, partial);
-  B2G_LAUNCH_CHECK();
-  k_bn_finalize<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, m, d, eps, momentum, mean, rstd, running_mean, running_var);
-  B2G_LAUNCH_CHECK();
-  return B2G_OK;
+  COL_WS_CHECK("bn_stats");
+  ColFin fin{};
+  fin.kind = 0; fin.m = m; fin.eps = eps; fin.momentum = momentum;
+  fin.mean = mean; fin.rstd = rstd; fin.running_mean = running_mean; fin.running_var = running_var;
+  return launch_col_reduce<0>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, (double*)ws, fin, (cudaStream_t)stream_);
 }
 
 /* out[c] = sum_r x[r, c]  (bias gradient of a linear layer), fp64 accumulation, fixed order */
 extern "C" int b2g_col_sums(const float* x, int64_t m, int d, float* out, void* ws, size_t ws_bytes, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(x && out && m > 0 && d_ok(d) && aligned16(x), "col_sums: bad args (m=%lld d=%d)", (long long)m, d);
-  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
-    set_error("col_sums: workspace too small");
-    return B2G_EWS;
-  }
-  double* partial = (double*)ws;
-  int parts = col_parts(m, d);
-  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
-  k_col_partial<0><<<parts, 256, smem, st>>>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, partial);
-  B2G_LAUNCH_CHECK();
-  k_colsum_finalize<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, d, out);
-  B2G_LAUNCH_CHECK();
-  return B2G_OK;
+  COL_WS_CHECK("col_sums");
+  ColFin fin{};
+  fin.kind = 2; fin.out = out;
+  return launch_col_reduce<0>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, (double*)ws, fin, (cudaStream_t)stream_);
 }
-
 
 /* Patient-partitioned BatchNorm (multi-GPU): each rank reduces its rows to fp64 column totals sums[2*d] = {sum x, sum x^2}
  * (b2g_bn_local_sums), the ranks all-reduce them, and b2g_bn_finalize_sums turns the global totals + global row count
  * into mean / rstd (+ running-stat update).  Backward: b2g_bn_bwd_local_sums gives {sum g, sum g*xhat}; after the
  * all-reduce b2g_bn_bwd_from_sums writes dx (m_total = global row count) and dgamma / dbeta. */
 extern "C" int b2g_bn_local_sums(const float* x, int64_t m, int d, double* sums, void* ws, size_t ws_bytes, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(x && sums && m > 0 && d_ok(d) && aligned16(x), "bn_local_sums: bad args");
-  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
-    set_error("bn_local_sums: workspace too small");
-    return B2G_EWS;
-  }
-  double* partial = (double*)ws;
-  int parts = col_parts(m, d);
-  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
-  k_col_partial<0><<<parts, 256, smem, st>>>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, partial);
-  B2G_LAUNCH_CHECK();
-  k_col_totals<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, d, sums);
-  B2G_LAUNCH_CHECK();
-  return B2G_OK;
+  COL_WS_CHECK("bn_local_sums");
+  ColFin fin{};
+  fin.kind = 3; fin.sums = sums;
+  return launch_col_reduce<0>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, (double*)ws, fin, (cudaStream_t)stream_);
 }
 
 extern "C" int b2g_bn_finalize_sums(const double* sums, int64_t m_total, int d, float eps, float momentum, float* mean, float* rstd,
@@ -501,20 +515,13 @@ extern "C" int b2g_bn_finalize_sums(const double* sums, int64_t m_total, int d, 
 extern "C" int b2g_bn_bwd_local_sums(const float* x, const float* dy, int64_t m, int d, const float* mean, const float* rstd,
                                      const float* gamma, const float* beta, int relu, float p_drop, uint64_t seed, uint64_t stream_id,
                                      double* sums, void* ws, size_t ws_bytes, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(m > 0 && d_ok(d) && x && dy && mean && rstd && gamma && beta && sums, "bn_bwd_local_sums: bad args");
-  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
-    set_error("bn_bwd_local_sums: workspace too small");
-    return B2G_EWS;
-  }
-  double* partial = (double*)ws;
-  int parts = col_parts(m, d);
-  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
-  k_col_partial<1><<<parts, 256, smem, st>>>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, partial);
-  B2G_LAUNCH_CHECK();
-  k_col_totals<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, d, sums);
-  B2G_LAUNCH_CHECK();
-  return B2G_OK;
+  B2G_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
+                "bn_bwd_local_sums: unaligned pointer");
+  COL_WS_CHECK("bn_bwd_local_sums");
+  ColFin fin{};
+  fin.kind = 3; fin.sums = sums;
+  return launch_col_reduce<1>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, (double*)ws, fin, (cudaStream_t)stream_);
 }
 
 extern "C" int b2g_bn_bwd_from_sums(const float* x, const float* dy, int64_t m, int64_t m_total, int d, const float* mean,
@@ -522,8 +529,10 @@ extern "C" int b2g_bn_bwd_from_sums(const float* x, const float* dy, int64_t m, 
                                     uint64_t stream_id, const double* sums, float* dx, float* dgamma, float* dbeta, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(m > 0 && m_total >= m && d_ok(d) && x && dy && mean && rstd && gamma && beta && sums && dx, "bn_bwd_from_sums: bad args");
-  int64_t n4 = m * d / 4;
-  k_bn_bwd_apply<<<ew_grid(n4), 256, 0, st>>>(x, dy, n4, m_total, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, 1, sums, dx);
+  B2G_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
+                "bn_bwd_from_sums: unaligned pointer");
+  int64_t n8 = m * d / 8;
+  k_bn_bwd_apply<<<ew_grid(n8), 256, 0, st>>>(x, dy, n8, m_total, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, 1, sums, dx);
   B2G_LAUNCH_CHECK();
   if (dgamma || dbeta) {
     k_sums_to_float<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(sums, d, dbeta, dgamma);
@@ -547,8 +556,8 @@ extern "C" int b2g_bn_apply(const float* x, int64_t m, int d, const float* mean,
   if (m == 0) return B2G_OK;
   B2G_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
                 "bn_apply: unaligned pointer");
-  int64_t n4 = m * d / 4;
-  k_bn_apply<<<ew_grid(n4), 256, 0, (cudaStream_t)stream_>>>(x, n4, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, y);
+  int64_t n8 = m * d / 8;
+  k_bn_apply<<<ew_grid(n8), 256, 0, (cudaStream_t)stream_>>>(x, n8, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, y);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }
@@ -558,21 +567,17 @@ extern "C" int b2g_bn_bwd(const float* x, const float* dy, int64_t m, int d, con
                           float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(m > 0 && d_ok(d) && x && dy && mean && rstd && gamma && beta && dx, "bn_bwd: bad args");
-  B2G_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx), "bn_bwd: unaligned pointer");
-  if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {
-    set_error("bn_bwd: workspace too small");
-    return B2G_EWS;
-  }
+  B2G_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
+                "bn_bwd: unaligned pointer");
+  COL_WS_CHECK("bn_bwd");
   double* partial = (double*)ws;
   double* sums = (double*)((char*)ws + align_up((size_t)MAX_PARTIALS * 2 * d * 8, 256));
-  int parts = col_parts(m, d);
-  size_t smem = (size_t)(256 / (d / 4)) * 2 * d * sizeof(double);
-  k_col_partial<1><<<parts, 256, smem, st>>>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, partial);
-  B2G_LAUNCH_CHECK();
-  k_bn_bwd_finalize<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(partial, parts, d, sums, dgamma, dbeta);
-  B2G_LAUNCH_CHECK();
-  int64_t n4 = m * d / 4;
-  k_bn_bwd_apply<<<ew_grid(n4), 256, 0, st>>>(x, dy, n4, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, batch_stats, sums, dx);
+  ColFin fin{};
+  fin.kind = 1; fin.sums = sums; fin.dgamma = dgamma; fin.dbeta = dbeta;
+  int rc = launch_col_reduce<1>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, partial, fin, st);
+  if (rc != B2G_OK) return rc;
+  int64_t n8 = m * d / 8;
+  k_bn_bwd_apply<<<ew_grid(n8), 256, 0, st>>>(x, dy, n8, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, batch_stats, sums, dx);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }
