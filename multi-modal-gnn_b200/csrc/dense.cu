@@ -195,12 +195,22 @@ __global__ void __launch_bounds__(256) k_sgemm_small(const float* __restrict__ A
 }
 constexpr int SMALL_M = 1024;
 
-// db[n] = sum_m dy[m, n] for a few hundred rows (sequential per column: deterministic)
-__global__ void k_colsum_small(const float* __restrict__ dy, int M, int N, float* __restrict__ db) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// db[n] = sum_m dy[m, n] for a few hundred rows: 32 columns per CTA, 8 row slices (one per warp, coalesced 128-byte row
+// segments, 8 loads in flight), slices combined in fixed order: deterministic
+__global__ void __launch_bounds__(256) k_colsum_small(const float* __restrict__ dy, int M, int N, float* __restrict__ db) {
+  __shared__ float sh[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int m = 0; m < M; ++m) s += __ldg(dy + (size_t)m * N + n);
+  if (n < N) {
+#pragma unroll 8
+    for (int m = slice; m < M; m += 8) s += __ldg(dy + (size_t)m * N + n);
+  }
+  sh[slice][lane] = s;
+  __syncthreads();
+  if (slice != 0 || n >= N) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) s += sh[k][lane];
   db[n] = s;
 }
 
@@ -341,7 +351,7 @@ extern "C" int b2g_linear_bwd_weight(const float* dy, const float* x, int64_t m,
     k_sgemm_small<true, false><<<g, 256, 0, st>>>(dy, x, nullptr, n, k, (int)m, dw, 0);
     B2G_LAUNCH_CHECK();
     if (db) {
-      k_colsum_small<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(dy, (int)m, n, db);
+      k_colsum_small<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(dy, (int)m, n, db);
       B2G_LAUNCH_CHECK();
     }
     return B2G_OK;

@@ -273,21 +273,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tf32(const __grid_const
   }
 }
 
-// out[i] = sum over CTAs of partial[c][i] (fixed order); optionally transposed: partial is [128][nb] = dW^T
+// out = sum over CTAs of partial[c] (fixed order); optionally transposed: partial[c] is [128][nb] = dW^T.
+// A thread owns 4 consecutive outputs (16-byte, fully coalesced loads: consecutive lanes read consecutive float4 of the
+// same partial record) for one of 8 slices of the CTA records; the 8 slices are combined in order through shared memory.
 __global__ void __launch_bounds__(256) k_wgrad_tc_reduce(const float* __restrict__ partial, int n_cta, int rows, int cols, int transpose,
                                                          float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);      // one warp per output element, lanes stride over the CTAs
-  if (i >= rows * cols) return;
-  float s = 0.f;
-  for (int c = lane; c < n_cta; c += 32) s += partial[(size_t)c * rows * cols + i];
-  s = warp_sum(s);
-  if (lane != 0) return;
+  __shared__ float4 sh[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int n4 = rows * cols / 4;
+  const int i4 = blockIdx.x * 32 + lane;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i4 < n4) {
+    const float4* src = reinterpret_cast<const float4*>(partial) + i4;
+#pragma unroll 4
+    for (int c = slice; c < n_cta; c += 8) {
+      const float4 v = __ldg(src + (size_t)c * n4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sh[slice][lane] = acc;
+  __syncthreads();
+  if (slice != 0 || i4 >= n4) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    const float4 v = sh[k][lane];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
   if (transpose) {
-    int r = i / cols, cc = i % cols;
-    out[(size_t)cc * rows + r] = s;
+    const int i = i4 * 4, r = i / cols, cc = i % cols;       // cols % 4 == 0: the 4 outputs share row r
+    out[(size_t)cc * rows + r] = acc.x;
+    out[(size_t)(cc + 1) * rows + r] = acc.y;
+    out[(size_t)(cc + 2) * rows + r] = acc.z;
+    out[(size_t)(cc + 3) * rows + r] = acc.w;
   } else {
-    out[i] = s;
+    reinterpret_cast<float4*>(out)[i4] = acc;
   }
 }
 
@@ -446,7 +465,7 @@ extern "C" int b2g_linear_bwd_weight_tc(const float* dy, const float* x, int64_t
   k_wgrad_tf32<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, prm);
   B2G_LAUNCH_CHECK();
   // partial[c] is [128][nb]: equals dW[N,K] when !swap (rows = n), dW^T when swap (rows = k, cols = n)
-  k_wgrad_tc_reduce<<<(unsigned)ceil_div(128 * nb, 8), 256, 0, st>>>(prm.partial, grid, 128, nb, swap ? 1 : 0, dw);
+  k_wgrad_tc_reduce<<<(unsigned)ceil_div(128 * nb / 4, 32), 256, 0, st>>>(prm.partial, grid, 128, nb, swap ? 1 : 0, dw);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

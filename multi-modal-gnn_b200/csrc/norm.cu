@@ -377,11 +377,27 @@ __global__ void __launch_bounds__(256) k_loss_partial(const float* __restrict__ 
   __shared__ unsigned long long sc[8];
   double s = 0;
   unsigned long long cnt = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
-    if (sup && !sup[i]) continue;
-    float wt = w ? __ldg(w + __ldg(lab + i)) : 1.f;
-    s += (double)(wt * loss_term(pred[i] - target[i], kind));
-    ++cnt;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < m; i0 += 4 * stride) {
+    float term[4];
+    bool on[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {            // 4 independent element chains in flight per thread
+      const int64_t i = i0 + u * stride;
+      on[u] = i < m && (!sup || sup[i]);
+      term[u] = 0.f;
+      if (on[u]) {
+        const float wt = w ? __ldg(w + __ldg(lab + i)) : 1.f;
+        term[u] = wt * loss_term(pred[i] - target[i], kind);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {            // element order i0, i0 + stride, ... : fixed
+      if (on[u]) {
+        s += (double)term[u];
+        ++cnt;
+      }
+    }
   }
   s = warp_sum(s);
 #pragma unroll
@@ -403,24 +419,47 @@ __global__ void __launch_bounds__(256) k_loss_partial(const float* __restrict__ 
   }
 }
 
-__global__ void k_loss_final(const double* __restrict__ part_sum, const unsigned long long* __restrict__ part_cnt, int n_part,
-                             float* __restrict__ loss, double* __restrict__ inv_count) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double t = 0;
-  unsigned long long c = 0;
-  for (int i = 0; i < n_part; ++i) {
+// totals of the per-CTA partials by one warp (lanes stride over the partials, fixed-order butterfly): every caller gets the
+// same bits
+__device__ __forceinline__ void loss_totals(const double* __restrict__ part_sum, const unsigned long long* __restrict__ part_cnt, int n_part,
+                                            int lane, double& t, unsigned long long& c) {
+  t = 0;
+  c = 0;
+  for (int i = lane; i < n_part; i += 32) {
     t += part_sum[i];
     c += part_cnt[i];
   }
-  double inv = 1.0 / (double)c;  // c == 0 -> inf -> loss NaN, like torch's mean over an empty selection
-  *loss = (float)(t * inv);
-  *inv_count = inv;
+  t = warp_sum(t);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
 }
 
+__global__ void k_loss_final(const double* __restrict__ part_sum, const unsigned long long* __restrict__ part_cnt, int n_part,
+                             float* __restrict__ loss) {
+  double t;
+  unsigned long long c;
+  loss_totals(part_sum, part_cnt, n_part, threadIdx.x & 31, t, c);
+  if (threadIdx.x == 0) *loss = (float)(t * (1.0 / (double)c));   // c == 0 -> inf -> loss NaN, like torch's mean over an empty selection
+}
+
+// gradient + (block 0) the loss value: every CTA re-derives the supervised count from the partial counts itself
 __global__ void __launch_bounds__(256) k_loss_grad(const float* __restrict__ pred, const float* __restrict__ target, const int64_t* __restrict__ lab,
                                                    const float* __restrict__ w, const uint8_t* __restrict__ sup, int64_t m, int kind,
-                                                   const double* __restrict__ inv_count, float* __restrict__ grad) {
-  const float inv = (float)(*inv_count);
+                                                   const double* __restrict__ part_sum, const unsigned long long* __restrict__ part_cnt,
+                                                   int n_part, float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ float inv_s;
+  if (threadIdx.x < 32) {
+    double t;
+    unsigned long long c;
+    loss_totals(part_sum, part_cnt, n_part, threadIdx.x, t, c);
+    if (threadIdx.x == 0) {
+      const double inv = 1.0 / (double)c;
+      inv_s = (float)inv;
+      if (blockIdx.x == 0) *loss = (float)(t * inv);
+    }
+  }
+  __syncthreads();
+  const float inv = inv_s;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
     float g = 0.f;
     if (!sup || sup[i]) {
@@ -644,15 +683,15 @@ extern "C" int b2g_weighted_loss(const float* pred, const float* target, const i
   }
   double* part_sum = (double*)ws;
   unsigned long long* part_cnt = (unsigned long long*)((char*)ws + align_up((size_t)MAX_PARTIALS * 8, 256));
-  double* inv_count = (double*)((char*)ws + 2 * align_up((size_t)MAX_PARTIALS * 8, 256));
   int parts = (int)ceil_div(m > 0 ? m : 1, 256 * 8);
   if (parts > MAX_PARTIALS) parts = MAX_PARTIALS;
   k_loss_partial<<<parts, 256, 0, st>>>(pred, target, lab, w, sup, m, kind, part_sum, part_cnt);
   B2G_LAUNCH_CHECK();
-  k_loss_final<<<1, 32, 0, st>>>(part_sum, part_cnt, parts, loss, inv_count);
-  B2G_LAUNCH_CHECK();
   if (grad && m > 0) {
-    k_loss_grad<<<ew_grid(m), 256, 0, st>>>(pred, target, lab, w, sup, m, kind, inv_count, grad);
+    k_loss_grad<<<ew_grid(m), 256, 0, st>>>(pred, target, lab, w, sup, m, kind, part_sum, part_cnt, parts, loss, grad);
+    B2G_LAUNCH_CHECK();
+  } else {
+    k_loss_final<<<1, 32, 0, st>>>(part_sum, part_cnt, parts, loss);
     B2G_LAUNCH_CHECK();
   }
   return B2G_OK;
