@@ -199,7 +199,7 @@ def run_ours(args):
     # BatchNorm statistics and replicated->local gradients are all-reduced so that N ranks compute what one GPU would
     # compute on the union graph (checked by tools/dist_check.py), plus one flat gradient all-reduce per step.
     D = importlib.import_module(PKG + ".dist")
-    dctx = D.DistContext() if world > 1 else None
+    dctx = D.DistContext(device=dev) if world > 1 else None
     g_host = pkg.synth.make_graph(spec, seed=42 + rank)
     masker = T.EdgeMasker(g_host, 0.7, 0.15, 0.15, 0.2, 42 + rank)
     torch.manual_seed(0)
@@ -318,7 +318,15 @@ def run_ours(args):
                 "traffic": None, "launches_per_step": calls, "avg_launch_ms": ms / calls, "share_of_step": a_share(ms, tot),
                 "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if peaks["source"] == "measured" else "fallback"}
 
+    if world > 1 and dctx.peer is not None:
+        dctx.peer.check()                          # a timed-out rendezvous would have produced garbage: fail loudly
     if rank == 0:
+        parallelism = None
+        if world > 1:
+            per_step = dctx.n_collectives_per_step or 0
+            parallelism = (f"patient-partitioned x{world}, exact mode: {per_step} exchanges per step (incl. the gradient all-reduce), "
+                           + (f"{dctx.n_peer_per_step} of them one-shot NVLink peer-memory kernels of libb2g (BatchNorm ones fused into the "
+                              f"reduction kernel), rest NCCL" if dctx.peer is not None else "all NCCL") + ", captured in the step's CUDA graph")
         edges_per_step = NUM_LAYERS * spec.directed_edges_per_layer * world
         line = {"metric": METRIC, "value": edges_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,7 +337,7 @@ def run_ours(args):
                                        f"{n_train} train pairs, 20% supervised, Adam",
                            "step": "Trainer.train_step: predict_lab_values fwd + weighted loss + bwd" + (" (one CUDA graph replay)" if use_graph else "") + " + Adam",
                            "l2": "flushed with a 256 MiB write before every timed step; per-step working set (>1 GB) also exceeds the 126 MB L2",
-                           "parallelism": (f"patient-partitioned x{world}, exact mode: {dctx.n_collectives // max(1, total_steps + e2e_steps + 2)} small all-reduces + 1 gradient all-reduce per step" if world > 1 else "single GPU")},
+                           "parallelism": (parallelism if world > 1 else "single GPU")},
                 "e2e": {"value": edges_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels, "final_loss": final_loss,

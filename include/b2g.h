@@ -200,6 +200,38 @@ int b2g_bn_bwd(const float* x, const float* dy, int64_t m, int d, const float* m
                const float* gamma, const float* beta, int relu, float p_drop, uint64_t seed,
                uint64_t stream_id, int batch_stats, float* dx, float* dgamma, float* dbeta, void* ws,
                size_t ws_bytes, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * (f) multi-GPU exchange over NVLink peer memory (replaces the NCCL launches of the
+ *     latency-bound all-reduces of the patient-partitioned mode -- csrc/peer.cuh, csrc/comm.cu)
+ * Setup (SYNC, once per process): every rank allocates its symmetric region and exports a CUDA-IPC handle,
+ * the host side exchanges the 64-byte handles (torch.distributed.all_gather_object), every rank maps its
+ * peers.  At most 8 ranks, all on one node.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b2g_comm b2g_comm_t;
+size_t b2g_comm_region_bytes(void);
+size_t b2g_comm_max_bytes(void);      /* largest payload of one b2g_comm_allreduce_* call */
+int b2g_comm_local_alloc(void** region, unsigned char* h_handle64);
+int b2g_comm_create(int rank, int world, void* local_region, const unsigned char* h_handles, b2g_comm_t** out);
+int b2g_comm_destroy(b2g_comm_t* comm);
+int b2g_comm_error(b2g_comm_t* comm);  /* SYNC: 1 if a wait timed out (a rank did not show up within ~1 s) */
+/* out[i] = sum over ranks of in[i] (in == out allowed), one-shot: every rank stores its payload in its own
+ * region, signals every peer, and adds everybody's payload in RANK ORDER (bit-identical on all ranks,
+ * deterministic).  Payload: a multiple of 16 bytes, 16-byte aligned, <= b2g_comm_max_bytes().  Every rank
+ * must issue the same calls in the same order.  Graph-capturable (sequence numbers live on the device). */
+int b2g_comm_allreduce_f32(b2g_comm_t* comm, const float* in, float* out, int64_t n, void* stream);
+int b2g_comm_allreduce_f64(b2g_comm_t* comm, const double* in, double* out, int64_t n, void* stream);
+/* Patient-partitioned BatchNorm with the exchange FUSED into the reduction kernel: the CTA that finishes last
+ * publishes this rank's fp64 column totals, meets the same CTA of every other rank, adds the totals in rank
+ * order and finalises -- one launch instead of local sums -> all-reduce -> finalize.  m = local rows,
+ * m_total = rows over all ranks; dgamma / dbeta receive the GLOBAL totals. */
+int b2g_bn_stats_sync(b2g_comm_t* comm, const float* x, int64_t m, int64_t m_total, int d, float eps,
+                      float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
+                      void* ws, size_t ws_bytes, void* stream);
+int b2g_bn_bwd_sync(b2g_comm_t* comm, const float* x, const float* dy, int64_t m, int64_t m_total, int d,
+                    const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
+                    float p_drop, uint64_t seed, uint64_t stream_id, float* dx, float* dgamma, float* dbeta,
+                    void* ws, size_t ws_bytes, void* stream);
+
 /* y = dropout(relu(x)) without normalisation (EdgeRegressionHead, model.py:377-380) and its backward
  * (dx = dy * mask * [y > 0]); in-place allowed. */
 int b2g_relu_dropout_fwd(const float* x, int64_t n, int relu, float p_drop, uint64_t seed, uint64_t stream_id,

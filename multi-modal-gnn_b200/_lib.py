@@ -117,6 +117,17 @@ _PROTOS = {
     "b2g_bn_apply": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_bn_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, c_int, _P, _P, _P,
                            _P, c_size_t, _P]),
+    "b2g_comm_region_bytes": (c_size_t, []),
+    "b2g_comm_max_bytes": (c_size_t, []),
+    "b2g_comm_local_alloc": (c_int, [ctypes.POINTER(c_void_p), ctypes.c_char_p]),
+    "b2g_comm_create": (c_int, [c_int, c_int, _P, ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "b2g_comm_destroy": (c_int, [_P]),
+    "b2g_comm_error": (c_int, [_P]),
+    "b2g_comm_allreduce_f32": (c_int, [_P, _P, _P, c_int64, _P]),
+    "b2g_comm_allreduce_f64": (c_int, [_P, _P, _P, c_int64, _P]),
+    "b2g_bn_stats_sync": (c_int, [_P, _P, c_int64, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "b2g_bn_bwd_sync": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, _P, _P, _P,
+                                _P, c_size_t, _P]),
     "b2g_relu_dropout_fwd": (c_int, [_P, c_int64, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_relu_dropout_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_dropout_mask": (c_int, [c_int64, c_float, c_uint64, c_uint64, _P, _P]),

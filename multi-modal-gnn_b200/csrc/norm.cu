@@ -3,7 +3,7 @@
 // weighted MAE/MSE (train.py:364-386), compute_regression_loss (model.py:579-612).
 // All reductions are two-stage and order-fixed (deterministic); column statistics accumulate in fp64.
 #include <atomic>
-#include "common.cuh"
+#include "peer.cuh"
 
 namespace {
 using namespace b2g;
@@ -50,6 +50,8 @@ struct ColFin {
   double* sums;                                       // kind 1, 3
   float *dgamma, *dbeta;                              // kind 1
   float* out;                                         // kind 2
+  int peer_on;                                        // multi-GPU: the column totals are summed over the ranks (peer.cuh)
+  PeerCtx peer;                                       //            before the finalisation, inside this kernel
 };
 
 __device__ unsigned int g_tickets[1024];   // zero at load; the last CTA of a launch resets its slot.  Slots rotate per launch
@@ -140,13 +142,40 @@ __global__ void __launch_bounds__(COL_THREADS) k_col_reduce(const float* __restr
     }
   }
   __syncthreads();
-  for (int cc = threadIdx.x; cc < d; cc += COL_THREADS) {
+  {
+    const int cc = threadIdx.x;                       // d <= 256 < COL_THREADS: one column per thread
+    const bool col = cc < d;
     double s0 = 0, s1 = 0;
-    for (int sl = 0; sl < n_slices; ++sl) {
-      s0 += comb[sl * outs + cc];
-      s1 += comb[sl * outs + d + cc];
+    if (col) {
+      for (int sl = 0; sl < n_slices; ++sl) {
+        s0 += comb[sl * outs + cc];
+        s1 += comb[sl * outs + d + cc];
+      }
     }
-    if (fin.kind == 0) {
+    if (fin.peer_on) {
+      // patient-partitioned BatchNorm: this rank's totals -> own symmetric slice, rendezvous with the same CTA of every
+      // other rank, global totals = sum in rank order of everybody's slice (bit-identical on all ranks)
+      const uint32_t seq = peer_next_seq(fin.peer, PEER_SLOT_BN);
+      const size_t off = peer_slice_off(PEER_SLOT_BN, seq & 1u);
+      double* mine = reinterpret_cast<double*>(fin.peer.base[fin.peer.rank] + off);
+      if (col) {
+        mine[cc] = s0;
+        mine[d + cc] = s1;
+      }
+      peer_signal_wait(fin.peer, PEER_SLOT_BN, seq);
+      if (col) {
+        s0 = s1 = 0;
+        for (int r = 0; r < fin.peer.world; ++r) {
+          const double* theirs = reinterpret_cast<const double*>(fin.peer.base[r] + off);
+          s0 += ld_volatile_f64(theirs + cc);
+          s1 += ld_volatile_f64(theirs + d + cc);
+        }
+      }
+      if (threadIdx.x == 0) peer_commit_seq(fin.peer, PEER_SLOT_BN, seq);
+    }
+    if (!col) {
+      // nothing to finalise
+    } else if (fin.kind == 0) {
       const double mm = (double)fin.m;
       const double mean_ = s0 / mm;
       double var = s1 / mm - mean_ * mean_;
@@ -577,6 +606,46 @@ extern "C" int b2g_bn_bwd_from_sums(const float* x, const float* dy, int64_t m, 
     k_sums_to_float<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(sums, d, dbeta, dgamma);
     B2G_LAUNCH_CHECK();
   }
+  return B2G_OK;
+}
+
+/* Fused multi-GPU variants (peer.cuh): the per-rank column totals are exchanged over NVLink peer memory by the last CTA
+ * of the reduction kernel itself -- statistics, exchange and finalisation are ONE launch (instead of local sums ->
+ * NCCL all-reduce -> finalize).  m = local rows, m_total = rows over all ranks.  dgamma / dbeta are the GLOBAL totals. */
+extern "C" const void* b2g_comm_ctx(const struct b2g_comm* c);
+
+extern "C" int b2g_bn_stats_sync(struct b2g_comm* comm, const float* x, int64_t m, int64_t m_total, int d, float eps, float momentum,
+                                 float* mean, float* rstd, float* running_mean, float* running_var, void* ws, size_t ws_bytes,
+                                 void* stream_) {
+  B2G_CHECK_ARG(comm && x && mean && rstd && m > 0 && m_total >= m && d_ok(d) && aligned16(x), "bn_stats_sync: bad args");
+  COL_WS_CHECK("bn_stats_sync");
+  ColFin fin{};
+  fin.kind = 0; fin.m = m_total; fin.eps = eps; fin.momentum = momentum;
+  fin.mean = mean; fin.rstd = rstd; fin.running_mean = running_mean; fin.running_var = running_var;
+  fin.peer_on = 1;
+  fin.peer = *reinterpret_cast<const PeerCtx*>(b2g_comm_ctx(comm));
+  return launch_col_reduce<0>(x, nullptr, m, d, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, (double*)ws, fin, (cudaStream_t)stream_);
+}
+
+extern "C" int b2g_bn_bwd_sync(struct b2g_comm* comm, const float* x, const float* dy, int64_t m, int64_t m_total, int d, const float* mean,
+                               const float* rstd, const float* gamma, const float* beta, int relu, float p_drop, uint64_t seed,
+                               uint64_t stream_id, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(comm && m > 0 && m_total >= m && d_ok(d) && x && dy && mean && rstd && gamma && beta && dx, "bn_bwd_sync: bad args");
+  B2G_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
+                "bn_bwd_sync: unaligned pointer");
+  COL_WS_CHECK("bn_bwd_sync");
+  double* partial = (double*)ws;
+  double* sums = (double*)((char*)ws + align_up((size_t)MAX_PARTIALS * 2 * d * 8, 256));
+  ColFin fin{};
+  fin.kind = 1; fin.sums = sums; fin.dgamma = dgamma; fin.dbeta = dbeta;
+  fin.peer_on = 1;
+  fin.peer = *reinterpret_cast<const PeerCtx*>(b2g_comm_ctx(comm));
+  int rc = launch_col_reduce<1>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, partial, fin, st);
+  if (rc != B2G_OK) return rc;
+  int64_t n8 = m * d / 8;
+  k_bn_bwd_apply<<<ew_grid(n8), 256, 0, st>>>(x, dy, n8, m_total, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, 1, sums, dx);
+  B2G_LAUNCH_CHECK();
   return B2G_OK;
 }
 

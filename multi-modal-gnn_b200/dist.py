@@ -27,22 +27,86 @@ from torch.autograd import Function
 from .heterodata import HeteroGraph
 
 
+class PeerComm:
+    """libb2g's peer-memory communicator (include/b2g.h section (f), csrc/peer.cuh): every rank's symmetric region is
+    mapped into every other rank of the node through CUDA IPC, and the small all-reduces of the step become one-shot
+    kernels that store / load over NVLink directly -- fused into the producing kernel for the BatchNorm statistics."""
+
+    def __init__(self, group, device: torch.device):
+        import ctypes
+        from . import _lib
+        self._lib_mod = _lib
+        lib = _lib.load()
+        self.lib = lib
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise _lib.B2GError("PeerComm supports at most 8 ranks (one NVSwitch node)")
+        region = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            _lib.check(lib.b2g_comm_local_alloc(ctypes.byref(region), handle), "b2g_comm_local_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)    # also the "everybody allocated" rendezvous
+            comm = ctypes.c_void_p()
+            _lib.check(lib.b2g_comm_create(self.rank, self.world, region, b"".join(handles), ctypes.byref(comm)), "b2g_comm_create")
+        self.handle = comm
+        self.max_bytes = int(lib.b2g_comm_max_bytes())
+        dist.barrier(group=group)          # every rank has mapped every region before the first kernel signals
+
+    def usable(self, t: torch.Tensor) -> bool:
+        nbytes = t.numel() * t.element_size()
+        return (t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.float64) and nbytes > 0
+                and nbytes % 16 == 0 and t.data_ptr() % 16 == 0 and nbytes <= self.max_bytes)
+
+    def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
+        fn = self.lib.b2g_comm_allreduce_f32 if t.dtype == torch.float32 else self.lib.b2g_comm_allreduce_f64
+        self._lib_mod.check(fn(self.handle, t.data_ptr(), t.data_ptr(), t.numel(), torch.cuda.current_stream().cuda_stream),
+                            "b2g_comm_allreduce")
+        return t
+
+    def check(self):
+        """SYNC.  Raises if a wait inside a kernel timed out (a rank did not arrive)."""
+        if self.lib.b2g_comm_error(self.handle):
+            raise self._lib_mod.B2GError("peer-memory exchange timed out: a rank did not reach the rendezvous")
+
+
 class DistContext:
-    def __init__(self, group=None, sharded_type: str = "patient"):
+    def __init__(self, group=None, sharded_type: str = "patient", device: Optional[torch.device] = None, peer: Optional[bool] = None):
+        """``device``: this rank's CUDA device -- enables the peer-memory communicator (NVLink loads / stores from our own
+        kernels) for the step's small SUM all-reduces unless ``peer=False`` / B2G_PEER_COMM=0; torch.distributed stays the
+        path for everything else (CPU tensors under gloo, integer and MAX reductions, oversized payloads)."""
+        import os
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.sharded_type = sharded_type
         self.global_rows: Dict[int, int] = {}      # local row count of the sharded type -> global row count
         self.n_collectives = 0
-        self.trace = [] if __import__("os").environ.get("B2G_TRACE_COLLECTIVES") else None   # debugging aid
+        self.n_peer = 0                            # how many of them went through the peer-memory kernels
+        self.n_collectives_per_step = None         # set by Trainer._capture: exchanges inside one captured step
+        self.n_peer_per_step = None
+        self.trace = [] if os.environ.get("B2G_TRACE_COLLECTIVES") else None   # debugging aid
+        if peer is None:
+            peer = os.environ.get("B2G_PEER_COMM", "1") != "0"
+        self.peer: Optional[PeerComm] = None
+        if peer and device is not None and torch.device(device).type == "cuda" and self.world > 1:
+            self.peer = PeerComm(self.group, torch.device(device))
 
     def all_reduce_(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
         if self.trace is not None:
             self.trace.append((self.n_collectives, tuple(t.shape), str(t.dtype)))
-        dist.all_reduce(t, op=op, group=self.group)
         self.n_collectives += 1
+        if self.peer is not None and op == dist.ReduceOp.SUM and self.peer.usable(t):
+            self.n_peer += 1
+            return self.peer.all_reduce_(t)
+        dist.all_reduce(t, op=op, group=self.group)
         return t
+
+    def count_fused(self):
+        """An exchange that ran inside a compute kernel (ops.SyncBNActDropFn on the peer path)."""
+        self.n_collectives += 1
+        self.n_peer += 1
 
     def global_row_count(self, local_rows: int, device) -> int:
         """Number of rows of the sharded node type over all ranks (one tiny all-reduce, cached)."""
@@ -89,7 +153,7 @@ class PartialToReplicatedManyFn(Function):
 
     @staticmethod
     def forward(ctx, dctx: DistContext, *xs):
-        flat = torch.cat([x.reshape(-1) for x in xs])
+        flat = _flat_padded([x.reshape(-1) for x in xs])
         dctx.all_reduce_(flat)
         outs, off = [], 0
         for x in xs:
@@ -112,13 +176,22 @@ class ReplicatedToLocalManyFn(Function):
 
     @staticmethod
     def backward(ctx, *gs):
-        flat = torch.cat([g.reshape(-1) for g in gs])
+        flat = _flat_padded([g.reshape(-1) for g in gs])
         ctx.dctx.all_reduce_(flat)
         outs, off = [], 0
         for g in gs:
             outs.append(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
         return (None, *outs)
+
+
+def _flat_padded(chunks):
+    """torch.cat of 1-D fp32 chunks, zero-padded to a multiple of 4 elements (16 bytes: the peer all-reduce's unit)."""
+    n = sum(int(c.numel()) for c in chunks)
+    pad = (-n) % 4
+    if pad:
+        chunks = list(chunks) + [torch.zeros(pad, dtype=chunks[0].dtype, device=chunks[0].device)]
+    return torch.cat(chunks)
 
 
 class ScaleGradFn(Function):
@@ -218,31 +291,37 @@ def globalize_degrees(graph_index, dctx: DistContext):
     graph_index._globalized = True
 
 
-def allreduce_gradients(params, dctx: DistContext):
-    """The step's gradient exchange: one flat SUM all-reduce.  Parameters whose gradient is None on every rank (dead
-    branches, SURVEY.md note N8) stay None so that Adam keeps skipping them like the reference does."""
+def gradient_pattern(params, dctx: DistContext):
+    """SYNC (host round trip).  Which parameters have a gradient on at least one rank -- static for a given model and
+    graph, so the trainer computes it once; parameters whose gradient is None on every rank (dead branches, SURVEY.md
+    note N8) stay None so that Adam keeps skipping them like the reference does."""
+    params = list(params)
+    if not params:
+        return []
+    present = torch.tensor([0 if p.grad is None else 1 for p in params], dtype=torch.int32, device=params[0].device)
+    dctx.all_reduce_(present, op=dist.ReduceOp.MAX)
+    return [bool(v) for v in present.tolist()]
+
+
+def allreduce_gradients(params, dctx: DistContext, present=None):
+    """The step's gradient exchange: one flat SUM all-reduce (cat -> all-reduce -> one multi-tensor copy back).  With a
+    precomputed ``present`` pattern there is no host synchronisation, so the call can be captured into the step's graph."""
     params = list(params)
     if not params:
         return
-    dev = params[0].device
-    present = torch.tensor([0 if p.grad is None else 1 for p in params], dtype=torch.int32, device=dev)
-    dctx.all_reduce_(present, op=dist.ReduceOp.MAX)
-    present = present.tolist()
-    chunks = []
-    for p, has in zip(params, present):
-        if has:
-            chunks.append((p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1))
-    if not chunks:
+    if present is None:
+        present = gradient_pattern(params, dctx)
+    used = [p for p, has in zip(params, present) if has]
+    if not used:
         return
-    flat = torch.cat(chunks)
+    for p in used:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    flat = _flat_padded([p.grad.reshape(-1) for p in used])
     dctx.all_reduce_(flat)
-    off = 0
-    for p, has in zip(params, present):
-        if has:
-            n = p.numel()
-            g = flat[off:off + n].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += n
+    views, off = [], 0
+    for p in used:
+        n = p.numel()
+        views.append(flat[off:off + n].view_as(p))
+        off += n
+    torch._foreach_copy_([p.grad for p in used], views)

@@ -310,15 +310,21 @@ class SyncBNActDropFn(Function):
         x, gamma, beta = _f32(x, "x"), _f32(gamma, "bn.weight"), _f32(beta, "bn.bias")
         m, d = x.shape
         dev = x.device
-        sums = torch.empty(2 * d, dtype=torch.float64, device=dev)
         ws = workspace(lib.b2g_bn_ws_bytes(d), dev)
-        cost(4 * m * d)
-        _run("b2g_bn_local_sums", lib.b2g_bn_local_sums, x.data_ptr(), m, d, sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
-        dctx.all_reduce_(sums)
         mean = torch.empty(d, dtype=torch.float32, device=dev)
         rstd = torch.empty(d, dtype=torch.float32, device=dev)
-        _run("b2g_bn_finalize_sums", lib.b2g_bn_finalize_sums, sums.data_ptr(), int(m_total), d, float(eps), float(momentum),
-             mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), _stream())
+        peer = getattr(dctx, "peer", None)
+        cost(4 * m * d)
+        if peer is not None:      # statistics + NVLink exchange + finalisation in ONE kernel (csrc/peer.cuh)
+            _run("b2g_bn_stats_sync", lib.b2g_bn_stats_sync, peer.handle, x.data_ptr(), m, int(m_total), d, float(eps), float(momentum),
+                 mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), ws.data_ptr(), ws.numel(), _stream())
+            dctx.count_fused()
+        else:
+            sums = torch.empty(2 * d, dtype=torch.float64, device=dev)
+            _run("b2g_bn_local_sums", lib.b2g_bn_local_sums, x.data_ptr(), m, d, sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            dctx.all_reduce_(sums)
+            _run("b2g_bn_finalize_sums", lib.b2g_bn_finalize_sums, sums.data_ptr(), int(m_total), d, float(eps), float(momentum),
+                 mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), _stream())
         y = torch.empty_like(x)
         cost(8 * m * d)
         _run("b2g_bn_apply", lib.b2g_bn_apply, x.data_ptr(), m, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
@@ -335,19 +341,27 @@ class SyncBNActDropFn(Function):
         dy = _f32(dy, "grad")
         m, d = x.shape
         dev = x.device
-        sums = torch.empty(2 * d, dtype=torch.float64, device=dev)
         ws = workspace(lib.b2g_bn_ws_bytes(d), dev)
+        dx = torch.empty_like(x)
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+        inv = 1.0 / dctx.world
+        peer = getattr(dctx, "peer", None)
+        if peer is not None:      # backward statistics + NVLink exchange fused into the reduction kernel, then dx
+            cost(20 * m * d)
+            _run("b2g_bn_bwd_sync", lib.b2g_bn_bwd_sync, peer.handle, x.data_ptr(), dy.data_ptr(), m, m_total, d, mean.data_ptr(),
+                 rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, p, seed, sid, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                 ws.data_ptr(), ws.numel(), _stream())
+            dctx.count_fused()
+            return dx, dgamma * inv, dbeta * inv, None, None, None, None, None, None, None, None, None, None
+        sums = torch.empty(2 * d, dtype=torch.float64, device=dev)
         cost(8 * m * d)
         _run("b2g_bn_bwd_local_sums", lib.b2g_bn_bwd_local_sums, x.data_ptr(), dy.data_ptr(), m, d, mean.data_ptr(), rstd.data_ptr(),
              gamma.data_ptr(), beta.data_ptr(), act, p, seed, sid, sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
         dctx.all_reduce_(sums)
-        dx = torch.empty_like(x)
-        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
         cost(12 * m * d)
         _run("b2g_bn_bwd_from_sums", lib.b2g_bn_bwd_from_sums, x.data_ptr(), dy.data_ptr(), m, m_total, d, mean.data_ptr(), rstd.data_ptr(),
              gamma.data_ptr(), beta.data_ptr(), act, p, seed, sid, sums.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
              _stream())
-        inv = 1.0 / dctx.world
         return dx, dgamma * inv, dbeta * inv, None, None, None, None, None, None, None, None, None, None
 
 

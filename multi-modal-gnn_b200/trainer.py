@@ -15,7 +15,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib, ops
-from .dist import DistContext, allreduce_gradients
+from .dist import DistContext, allreduce_gradients, gradient_pattern
 from .model import compute_regression_loss
 
 
@@ -130,9 +130,8 @@ class Trainer:
         self.lab_weights = self._compute_lab_weights()
         # called between backward and optimizer.step: the multi-GPU gradient all-reduce
         # (the sharded node type's embedding rows are rank-local: their gradients are never exchanged)
-        self.grad_hook = (lambda: allreduce_gradients(
-            [p for n, p in self.model.named_parameters() if not n.startswith(f"embeddings.{self.dist.sharded_type}.")],
-            self.dist)) if self.dist is not None else None
+        self._grad_pattern = None       # which exchanged parameters have a gradient on some rank (static; one host sync)
+        self.grad_hook = self._exchange_gradients if self.dist is not None else None
         self._use_graph, self._graph = False, None
         self.graph_kernel_nodes = 0
 
@@ -160,6 +159,15 @@ class Trainer:
         ei, ev = self.masker.split_edges("train")
         return compute_lab_weights(ei[1], ev, int(self.data["lab"].num_nodes), self.dist)
 
+    def _exchanged_params(self):
+        return [p for n, p in self.model.named_parameters() if not n.startswith(f"embeddings.{self.dist.sharded_type}.")]
+
+    def _exchange_gradients(self):
+        params = self._exchanged_params()
+        if self._grad_pattern is None or len(self._grad_pattern) != len(params):
+            self._grad_pattern = gradient_pattern(params, self.dist)
+        allreduce_gradients(params, self.dist, self._grad_pattern)
+
     # ---- CUDA graph mode ------------------------------------------------------------------------------------------
     def enable_cuda_graph(self, enabled: bool = True):
         """Capture forward + loss + backward of the training step into one CUDA graph (the step is ~270 short launches
@@ -177,7 +185,9 @@ class Trainer:
         if self.dist is not None:
             # global mean over the supervised pairs of all ranks = sum_r (n_r / n) * local mean_r
             n_local = sup.sum().to(torch.float32)
-            n_total = self.dist.all_reduce_(n_local.clone())
+            cnt = torch.zeros(4, dtype=torch.float32, device=loss.device)      # 16 bytes: eligible for the peer-memory path
+            cnt[0] = n_local
+            n_total = self.dist.all_reduce_(cnt)[0]
             loss = torch.nan_to_num(loss) * (n_local / n_total)
         return loss
 
@@ -185,7 +195,9 @@ class Trainer:
         """Loss of the whole (partitioned) batch: the per-rank terms of _loss_of summed over ranks."""
         if self.dist is None:
             return loss
-        return self.dist.all_reduce_(loss.detach().clone())
+        buf = torch.zeros(4, dtype=torch.float32, device=loss.device)
+        buf[0] = loss.detach()
+        return self.dist.all_reduce_(buf)[0]
 
     def _capture(self, pi, li, ev, sup):
         model, dev = self.model, self.device
@@ -200,6 +212,8 @@ class Trainer:
             for _ in range(2):
                 self.optimizer.zero_grad(set_to_none=True)
                 self._loss_of(model.predict_lab_values(self.data, pi, li), ev, li, sup_static).backward()
+            if self.grad_hook is not None:                  # learn the (static) gradient pattern outside the capture
+                self._grad_pattern = gradient_pattern(self._exchanged_params(), self.dist)
         torch.cuda.current_stream().wait_stream(side)
         with torch.no_grad():                               # the warm-up must not count as training steps
             sd = model.state_dict()
@@ -209,10 +223,16 @@ class Trainer:
         graph = torch.cuda.CUDAGraph()
         lib = _lib.load()
         before = int(lib.b2g_launch_count())
+        coll0 = (self.dist.n_collectives, self.dist.n_peer) if self.dist is not None else None
         with torch.cuda.graph(graph):
             loss = self._loss_of(model.predict_lab_values(self.data, pi, li), ev, li, sup_static)
             loss.backward()
+            if self.grad_hook is not None:                  # the gradient exchange is part of the captured step
+                self.grad_hook()
         self.graph_kernel_nodes = int(lib.b2g_launch_count()) - before      # libb2g kernels replayed per step
+        if self.dist is not None:
+            self.dist.n_collectives_per_step = self.dist.n_collectives - coll0[0]
+            self.dist.n_peer_per_step = self.dist.n_peer - coll0[1]
         with torch.no_grad():                               # capture does not execute; make sure buffers are unchanged
             for k, v in buffers.items():
                 sd[k].copy_(v)
@@ -225,8 +245,6 @@ class Trainer:
         g["sup"].copy_(sup, non_blocking=True)
         self.model._seed_buffer.fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
         g["graph"].replay()
-        if self.grad_hook is not None:
-            self.grad_hook()
         self.optimizer.step()
         return g["loss"]
 

@@ -812,3 +812,67 @@ def test_fused_decoder_tensor_core_backward(m, p_drop, frac, dev):
     assert float((row_err > 5e-3 * ref[0].abs().max()).float().mean()) <= 0.02
     out2 = run(lib.b2g_decoder_bwd_tc)
     assert torch.equal(out[0], out2[0]) and torch.equal(out[2], out2[2])
+
+
+# ------------------------------------------------------------------------------------------------------
+# (f) peer-memory communicator: on one GPU (world = 1) the exchange degenerates to "sum of my own slice", which pins the
+#     slot / parity / sequence bookkeeping and the fused BatchNorm kernels; the 2-GPU run is tools/dist_check.py
+# ------------------------------------------------------------------------------------------------------
+def test_peer_comm_single_rank_allreduce_and_fused_batchnorm(dev):
+    import ctypes
+    pkg, G, ops, M, T, L = _mods()
+    lib = L.load()
+    region, handle, comm = ctypes.c_void_p(), ctypes.create_string_buffer(64), ctypes.c_void_p()
+    L.check(lib.b2g_comm_local_alloc(ctypes.byref(region), handle))
+    L.check(lib.b2g_comm_create(0, 1, region, bytes(handle.raw), ctypes.byref(comm)))
+    try:
+        gen = torch.Generator().manual_seed(5)
+        for n, dt in ((4, torch.float32), (512, torch.float64), (460 * 128, torch.float32), (1_000_000, torch.float32)):
+            a = torch.randn(n, generator=gen, dtype=dt).to(dev)
+            fn = lib.b2g_comm_allreduce_f32 if dt == torch.float32 else lib.b2g_comm_allreduce_f64
+            for _ in range(3):                      # both parities, advancing sequence numbers
+                out = torch.full_like(a, float("nan"))
+                L.check(fn(comm, a.data_ptr(), out.data_ptr(), n, None))
+                assert torch.equal(out, a)
+        big = torch.zeros(int(lib.b2g_comm_max_bytes()) // 4 + 4, device=dev)
+        assert lib.b2g_comm_allreduce_f32(comm, big.data_ptr(), big.data_ptr(), big.numel(), None) == -1   # over the one-shot limit
+        odd = torch.zeros(6, device=dev)
+        assert lib.b2g_comm_allreduce_f32(comm, odd.data_ptr(), odd.data_ptr(), 6, None) == -1             # not a multiple of 16 bytes
+
+        m, d = 3000, 128
+        x, dy = torch.randn(m, d, generator=gen).to(dev), torch.randn(m, d, generator=gen).to(dev)
+        gamma, beta = torch.rand(d, generator=gen).to(dev) + 0.5, torch.randn(d, generator=gen).to(dev)
+        ws = torch.empty(lib.b2g_bn_ws_bytes(d), dtype=torch.uint8, device=dev)
+
+        def stats(sync):
+            mean, rstd = torch.empty(d, device=dev), torch.empty(d, device=dev)
+            rm, rv = torch.zeros(d, device=dev), torch.ones(d, device=dev)
+            if sync:
+                L.check(lib.b2g_bn_stats_sync(comm, x.data_ptr(), m, m, d, 1e-5, 0.1, mean.data_ptr(), rstd.data_ptr(), rm.data_ptr(),
+                                              rv.data_ptr(), ws.data_ptr(), ws.numel(), None))
+            else:
+                L.check(lib.b2g_bn_stats(x.data_ptr(), m, d, 1e-5, 0.1, mean.data_ptr(), rstd.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), None))
+            return mean, rstd, rm, rv
+
+        a, b = stats(False), stats(True)
+        assert all(torch.equal(u, v) for u, v in zip(a, b))
+        mean, rstd = a[0], a[1]
+
+        def bwd(sync):
+            dx, dg, db = torch.empty_like(x), torch.empty(d, device=dev), torch.empty(d, device=dev)
+            if sync:
+                L.check(lib.b2g_bn_bwd_sync(comm, x.data_ptr(), dy.data_ptr(), m, m, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                            beta.data_ptr(), 1, 0.2, 77, 5, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), None))
+            else:
+                L.check(lib.b2g_bn_bwd(x.data_ptr(), dy.data_ptr(), m, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                       1, 0.2, 77, 5, 1, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), None))
+            return dx, dg, db
+
+        a, b = bwd(False), bwd(True)
+        assert all(torch.equal(u, v) for u, v in zip(a, b))
+        torch.cuda.synchronize()
+        assert lib.b2g_comm_error(comm) == 0
+    finally:
+        L.check(lib.b2g_comm_destroy(comm))
