@@ -195,11 +195,13 @@ int b2g_bn_apply(const float* x, int64_t m, int d, const float* mean, const floa
                  const float* beta, int relu, float p_drop, uint64_t seed, uint64_t stream_id, float* y,
                  void* stream);
 /* backward of the above.  Phase 1 (train mode only) reduces dgamma = sum(g * xhat), dbeta = sum(g) with
- * g = dy * mask * relu'; phase 2 writes dx.  In eval mode (batch_stats == 0) dx = g * gamma * rstd. */
+ * g = dy * mask * relu'; phase 2 writes dx.  In eval mode (batch_stats == 0) dx = g * gamma * rstd.
+ * dx_colsum (optional, [d]): column sums of dx, produced by the same pass that writes dx -- the bias gradient
+ * of the nn.Linear whose output was normalised (model.py:93-101), which would otherwise re-read dx. */
 int b2g_bn_bwd(const float* x, const float* dy, int64_t m, int d, const float* mean, const float* rstd,
                const float* gamma, const float* beta, int relu, float p_drop, uint64_t seed,
-               uint64_t stream_id, int batch_stats, float* dx, float* dgamma, float* dbeta, void* ws,
-               size_t ws_bytes, void* stream);
+               uint64_t stream_id, int batch_stats, float* dx, float* dgamma, float* dbeta, float* dx_colsum,
+               void* ws, size_t ws_bytes, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * (f) multi-GPU exchange over NVLink peer memory (replaces the NCCL launches of the
  *     latency-bound all-reduces of the patient-partitioned mode -- csrc/peer.cuh, csrc/comm.cu)
@@ -230,7 +232,7 @@ int b2g_bn_stats_sync(b2g_comm_t* comm, const float* x, int64_t m, int64_t m_tot
 int b2g_bn_bwd_sync(b2g_comm_t* comm, const float* x, const float* dy, int64_t m, int64_t m_total, int d,
                     const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
                     float p_drop, uint64_t seed, uint64_t stream_id, float* dx, float* dgamma, float* dbeta,
-                    void* ws, size_t ws_bytes, void* stream);
+                    float* dx_colsum, void* ws, size_t ws_bytes, void* stream);
 
 /* y = dropout(relu(x)) without normalisation (EdgeRegressionHead, model.py:377-380) and its backward
  * (dx = dy * mask * [y > 0]); in-place allowed. */

@@ -115,7 +115,7 @@ _PROTOS = {
                                      _P, _P]),
     "b2g_bn_eval_stats": (c_int, [_P, _P, c_int, c_float, _P, _P, _P]),
     "b2g_bn_apply": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, _P, _P]),
-    "b2g_bn_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, c_int, _P, _P, _P,
+    "b2g_bn_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, c_int, _P, _P, _P, _P,
                            _P, c_size_t, _P]),
     "b2g_comm_region_bytes": (c_size_t, []),
     "b2g_comm_max_bytes": (c_size_t, []),
@@ -126,7 +126,7 @@ _PROTOS = {
     "b2g_comm_allreduce_f32": (c_int, [_P, _P, _P, c_int64, _P]),
     "b2g_comm_allreduce_f64": (c_int, [_P, _P, _P, c_int64, _P]),
     "b2g_bn_stats_sync": (c_int, [_P, _P, c_int64, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "b2g_bn_bwd_sync": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, _P, _P, _P,
+    "b2g_bn_bwd_sync": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, _P, _P, _P, _P,
                                 _P, c_size_t, _P]),
     "b2g_relu_dropout_fwd": (c_int, [_P, c_int64, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_relu_dropout_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, c_uint64, c_uint64, _P, _P]),

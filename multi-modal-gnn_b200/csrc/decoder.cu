@@ -195,11 +195,27 @@ __global__ void __launch_bounds__(TCD_THREADS, TCD_MIN_CTAS) k_decoder_fwd_tc(co
   const int row = (warp & 3) * 32 + lane;                    // ... of tile row `row` (= TMEM lane)
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   uint32_t phase = 0;
+  // pair indices of this warp's 16 rows, fetched one tile ahead (they stream from HBM: ~1 us of latency otherwise exposed)
+  int nxt_p = -1, nxt_l = 0;
+  {
+    const int64_t ig = (int64_t)blockIdx.x * TILE_M + warp * 16 + lane;
+    if (lane < 16 && ig < M) {
+      nxt_p = (int)__ldg(pi + ig);
+      nxt_l = (int)__ldg(li + ig);
+    }
+  }
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    {  // this warp's 16 pairs: indices loaded once (coalesced), rows gathered 4 at a time by 8 lanes each
-      const int64_t ig = t * TILE_M + warp * 16 + lane;
-      const bool lv = lane < 16 && ig < M;
-      const int my_p = lv ? (int)__ldg(pi + ig) : -1, my_l = lv ? (int)__ldg(li + ig) : 0;
+    {  // this warp's 16 pairs: rows gathered 4 at a time by 8 lanes each
+      const int my_p = nxt_p, my_l = nxt_l;
+      {
+        const int64_t ig = (t + gridDim.x) * TILE_M + warp * 16 + lane;
+        nxt_p = -1;
+        nxt_l = 0;
+        if (lane < 16 && ig < M) {
+          nxt_p = (int)__ldg(pi + ig);
+          nxt_l = (int)__ldg(li + ig);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = 4 * j + q;

@@ -12,7 +12,10 @@
 //            per tile into one of two TMEM accumulators; tcgen05.commit releases the smem stage and
 //            publishes the accumulator
 //   warp 2   TMEM allocator / deallocator
-//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> + bias (+ previous Y when accumulating) -> 128-bit stores
+//   warps 4-7 epilogue: tcgen05.ld 32x32b (lane = row) -> registers -> a padded per-warp staging tile in shared memory ->
+//            re-read with 8 lanes per 128-byte row segment -> + bias (+ previous Y when accumulating) -> 128-bit stores
+//            that cover 4 whole row segments per instruction (a thread-per-row store touches 32 lines per instruction
+//            and made the L1 tag stage, not HBM, the bound of this kernel)
 #include "tc_common.cuh"
 
 namespace {
@@ -20,6 +23,9 @@ using namespace b2g;
 
 constexpr int TC_THREADS = 256;
 constexpr int SUB_BYTES = TILE_M * KB * 4;      // one [128 rows x 128 B] sub-tile of X = 16 KB
+constexpr int STG_ROW = 128 + 16;               // staging row: 32 floats + 16 B pad (conflict-free 16-byte accesses)
+constexpr int STG_WARP = 32 * STG_ROW;          // per epilogue warp: 32 rows x 32 columns
+constexpr int STG_BYTES = 4 * STG_WARP;
 
 struct TcParams {
   const float* bias;   // [N] or null
@@ -29,9 +35,11 @@ struct TcParams {
   int accumulate;
   int tmem_cols;       // 2 * N rounded to a power of two >= 32
   int stages;          // X ring depth: 2 when it fits in shared memory, else 1
+  int staged;          // epilogue through the shared-memory staging tile (coalesced stores) when it fits, else direct
 };
 
-// dynamic smem layout (1024-byte aligned): W sub-tiles [K/32][N rows x 128 B] | X stages [2][K/32][128 rows x 128 B]
+// dynamic smem layout (1024-byte aligned): W sub-tiles [K/32][N rows x 128 B] | X stages [2][K/32][128 rows x 128 B] |
+// epilogue staging [4 warps][32 rows x 144 B]
 __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_constant__ CUtensorMap map_x,
                                                                const __grid_constant__ CUtensorMap map_w, TcParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -45,6 +53,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
   // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window
   uint8_t* smem_w = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   uint8_t* smem_x = smem_w + w_bytes;
+  uint8_t* smem_stg = smem_x + (size_t)prm.stages * x_bytes;
   const int64_t n_tiles = (prm.m + TILE_M - 1) / TILE_M;
 
   if (threadIdx.x == 0) {
@@ -120,29 +129,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
       const uint32_t ph = (it >> 1) & 1;
       mbar_wait(&bar_tfull[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t row = t * TILE_M + q * 32 + lane;
+      const int64_t row0 = t * TILE_M + q * 32;          // first row of this warp's 32-row slab
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * prm.n);
+      uint8_t* stg = smem_stg + q * STG_WARP;
+      const int so = lane & 7, sq = lane >> 3;             // store phase: 16-byte chunk so of row 4j + sq
       for (int c0 = 0; c0 < prm.n; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < prm.m) {
-          float* dst = prm.y + (size_t)row * prm.n + c0;
+        if (!prm.staged) {                                 // no room for the staging tile: thread-per-row stores
+          if (row0 + lane < prm.m) {
+            float* dst = prm.y + (size_t)(row0 + lane) * prm.n + c0;
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                                   __uint_as_float(r[4 * v + 3]));
-            if (prm.bias) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(prm.bias + c0) + v);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            for (int v = 0; v < 8; ++v) {
+              float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                     __uint_as_float(r[4 * v + 3]));
+              if (prm.bias) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(prm.bias + c0) + v);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (prm.accumulate) {
+                float4 p = *(reinterpret_cast<const float4*>(dst) + v);
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+              }
+              *(reinterpret_cast<float4*>(dst) + v) = o;
             }
+          }
+          continue;
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          *reinterpret_cast<float4*>(stg + lane * STG_ROW + v * 16) =
+              make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+        __syncwarp();
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (prm.bias) b = __ldg(reinterpret_cast<const float4*>(prm.bias + c0) + so);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = 4 * j + sq;
+          if (row0 + rr < prm.m) {
+            float4 o = *reinterpret_cast<const float4*>(stg + rr * STG_ROW + so * 16);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            float4* dst = reinterpret_cast<float4*>(prm.y + (size_t)(row0 + rr) * prm.n + c0) + so;
             if (prm.accumulate) {
-              float4 p = *(reinterpret_cast<const float4*>(dst) + v);
+              const float4 p = *dst;
               o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
             }
-            *(reinterpret_cast<float4*>(dst) + v) = o;
+            *dst = o;
           }
         }
+        __syncwarp();                                      // the next chunk overwrites the staging tile
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -374,9 +410,17 @@ extern "C" int b2g_transpose(const float* in, int rows, int cols, float* out, vo
 }
 
 namespace {
-inline int tc_stages(int n, int k) {          // 2 X stages if they fit next to the resident W, else 1, else unsupported (0)
+inline size_t tc_smem(int n, int k, int st, bool staged) {
+  return (size_t)n * k * 4 + (size_t)st * TILE_M * k * 4 + (staged ? STG_BYTES : 0) + 1024;
+}
+// 2 X stages if they fit next to the resident W, else 1, else unsupported (0); the epilogue staging tile is dropped before a stage is
+inline int tc_stages(int n, int k, bool* staged = nullptr) {
   for (int st = 2; st >= 1; --st)
-    if ((size_t)n * k * 4 + (size_t)st * TILE_M * k * 4 + 1024 <= 227 * 1024) return st;
+    for (int sg = 1; sg >= 0; --sg)
+      if (tc_smem(n, k, st, sg != 0) <= 227 * 1024) {
+        if (staged) *staged = sg != 0;
+        return st;
+      }
   return 0;
 }
 }  // namespace
@@ -401,8 +445,10 @@ extern "C" int b2g_linear_fwd_tc(const float* x, const float* w, const float* bi
   int cols = 32;
   while (cols < 2 * n) cols <<= 1;
   prm.tmem_cols = cols;
-  prm.stages = tc_stages(n, k);
-  const size_t smem = (size_t)n * k * 4 + (size_t)prm.stages * TILE_M * k * 4 + 1024;
+  bool staged = false;
+  prm.stages = tc_stages(n, k, &staged);
+  prm.staged = staged ? 1 : 0;
+  const size_t smem = tc_smem(n, k, prm.stages, staged);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     B2G_CUDA(cudaFuncSetAttribute(k_linear_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_col_reduce(const float* __restr
   if (MODE == 1) {
     ld8(mean + c, mu); ld8(rstd + c, rsd); ld8(gamma + c, ga); ld8(beta + c, be);
   }
-#pragma unroll 2
+#pragma unroll(MODE == 0 ? 4 : 2)
   for (int64_t r = (int64_t)blockIdx.x * rpp + rs; r < m; r += (int64_t)gridDim.x * rpp) {
     const size_t off = (size_t)r * d + c;
     float xs[8];
@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(COL_THREADS) k_col_reduce(const float* __restr
     const int o = idx % outs, sl = (idx / outs) % n_slices;
     if (idx < outs * n_slices) {
       double acc = 0;
-#pragma unroll 8
-      for (int p = sl; p < n_part; p += n_slices) acc += __ldcg(partial + (size_t)p * outs + o);
+#pragma unroll 16
+      for (int p = sl; p < n_part; p += n_slices) acc += __ldcg(partial + (size_t)p * outs + o);   // 16 L2 loads in flight
       comb[sl * outs + o] = acc;
     }
   }
@@ -235,33 +235,49 @@ __global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __res
 // Element-wise passes: a thread owns 8 consecutive elements (one Philox call, two 16-byte accesses).  256 threads x 8
 // elements is a multiple of every supported d, so a thread's columns -- and its 8 x 4 parameters -- never change over the
 // grid-stride loop.
-__global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ x, int64_t n8, int d, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256, 3) k_bn_apply(const float* __restrict__ x, int64_t n8, int d, const float* __restrict__ mean,
                                                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                   int act, float p_drop, uint64_t seed, uint64_t sid, float* __restrict__ y) {
   if (p_drop > 0.f) resolve_seed(seed, sid);
   const int c = (int)((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8) % d);
   float mu[8], rs[8], ga[8], be[8];
   ld8(mean + c, mu); ld8(rstd + c, rs); ld8(gamma + c, ga); ld8(beta + c, be);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
-    float v[8];
-    ld8(x + i * 8, v);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += 2 * stride) {
+    float v[2][8];
+    const bool second = i0 + stride < n8;          // two octets per trip: twice the bytes in flight per thread
+    ld8(x + i0 * 8, v[0]);
+    if (second) ld8(x + (i0 + stride) * 8, v[1]);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = act_fwd(fmaf((v[e] - mu[e]) * rs[e], ga[e], be[e]), act);
-    if (p_drop > 0.f) {
-      float mk[8];
-      dropout_scale8(seed, sid, (uint64_t)i, p_drop, mk);
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !second) break;
+      const int64_t i = i0 + u * stride;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] *= mk[e];
+      for (int e = 0; e < 8; ++e) v[u][e] = act_fwd(fmaf((v[u][e] - mu[e]) * rs[e], ga[e], be[e]), act);
+      if (p_drop > 0.f) {
+        float mk[8];
+        dropout_scale8(seed, sid, (uint64_t)i, p_drop, mk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[u][e] *= mk[e];
+      }
+      st8(y + i * 8, v[u]);
     }
-    st8(y + i * 8, v);
   }
 }
 
-__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, int64_t n8, int64_t m, int d,
+// dx of BatchNorm(+act+dropout).  One CTA of 512 threads per SM, grid-stride over 8-element octets (a thread's columns
+// never change).  Optionally also the column sums of dx (= the bias gradient of the Linear that produced x, which would
+// otherwise cost another full pass over dx): per-thread fp64 sums -> per-CTA record -> the last CTA (ticket) adds the
+// records in CTA order: deterministic.
+constexpr int BWA_THREADS = 512;
+__global__ void __launch_bounds__(BWA_THREADS, 1) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, int64_t n8, int64_t m, int d,
                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta, int act, float p_drop,
                                                       uint64_t seed, uint64_t sid, int batch_stats, const double* __restrict__ sums,
-                                                      float* __restrict__ dx) {
+                                                      float* __restrict__ dx, double* __restrict__ cs_partial, float* __restrict__ colsum,
+                                                      int ticket_slot) {
+  extern __shared__ double dyn_cs[];             // [BWA_THREADS][8]   (column-sum variant only)
+  __shared__ int is_last;
   if (p_drop > 0.f) resolve_seed(seed, sid);
   const float inv_m = 1.0f / (float)m;
   const int c = (int)((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8) % d);
@@ -272,24 +288,81 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
     sg[e] = batch_stats ? (float)sums[c + e] * inv_m : 0.f;
     sgx[e] = batch_stats ? (float)sums[d + c + e] * inv_m : 0.f;
   }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
-    float xs[8], g[8];
-    ld8(x + i * 8, xs);
-    ld8(dy + i * 8, g);
-    if (p_drop > 0.f) {
-      float mk[8];
-      dropout_scale8(seed, sid, (uint64_t)i, p_drop, mk);
+  double cs[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) g[e] *= mk[e];
+  for (int e = 0; e < 8; ++e) cs[e] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += 2 * stride) {
+    float xs[2][8], g[2][8];
+    const bool second = i0 + stride < n8;          // two octets per trip: twice the bytes in flight per thread
+    ld8(x + i0 * 8, xs[0]);
+    ld8(dy + i0 * 8, g[0]);
+    if (second) {
+      ld8(x + (i0 + stride) * 8, xs[1]);
+      ld8(dy + (i0 + stride) * 8, g[1]);
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xh = (xs[e] - mu[e]) * rs[e];
-      g[e] *= act_grad(fmaf(xh, ga[e], be[e]), act);
-      g[e] = batch_stats ? ga[e] * rs[e] * (g[e] - sg[e] - xh * sgx[e]) : ga[e] * rs[e] * g[e];
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !second) break;
+      const int64_t i = i0 + u * stride;
+      if (p_drop > 0.f) {
+        float mk[8];
+        dropout_scale8(seed, sid, (uint64_t)i, p_drop, mk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[u][e] *= mk[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xs[u][e] - mu[e]) * rs[e];
+        float gg = g[u][e] * act_grad(fmaf(xh, ga[e], be[e]), act);
+        g[u][e] = batch_stats ? ga[e] * rs[e] * (gg - sg[e] - xh * sgx[e]) : ga[e] * rs[e] * gg;
+        cs[e] += (double)g[u][e];
+      }
+      st8(dx + i * 8, g[u]);
     }
-    st8(dx + i * 8, g);
   }
+  if (colsum == nullptr) return;
+  // ---- column sums of dx: threads t and t' share columns iff t = t' (mod d/8) ----
+  const int tpr = d >> 3;                           // 4 .. 32 threads cover one row
+  // serial, fixed-order accumulation over the BWA_THREADS / tpr threads of each column set, done by the first tpr threads
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dyn_cs[threadIdx.x * 8 + e] = cs[e];
+  __syncthreads();
+  if ((int)threadIdx.x < tpr) {
+    double tot[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) tot[e] = 0.0;
+    for (int t = threadIdx.x; t < BWA_THREADS; t += tpr)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tot[e] += dyn_cs[t * 8 + e];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs_partial[(size_t)blockIdx.x * d + threadIdx.x * 8 + e] = tot[e];
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&g_tickets[ticket_slot], 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int n_part = gridDim.x;
+  const int n_slices = BWA_THREADS / d;             // d = 256: 2 ... d = 32: 16
+  {
+    const int col = threadIdx.x % d, sl = threadIdx.x / d;
+    double acc = 0;
+#pragma unroll 16
+    for (int p = sl; p < n_part; p += n_slices) acc += __ldcg(cs_partial + (size_t)p * d + col);
+    dyn_cs[sl * d + col] = acc;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < d) {
+    double t = 0;
+    for (int sl = 0; sl < n_slices; ++sl) t += dyn_cs[sl * d + threadIdx.x];
+    colsum[threadIdx.x] = (float)t;
+  }
+  if (threadIdx.x == 0) g_tickets[ticket_slot] = 0u;
 }
 
 // ---- ReLU / Dropout --------------------------------------------------------------------------------------------
@@ -534,6 +607,21 @@ inline bool d_ok(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 
 extern "C" size_t b2g_bn_ws_bytes(int d) { return align_up((size_t)MAX_PARTIALS * 2 * d * 8, 256) + align_up((size_t)2 * d * 8, 256); }
 
+// dx pass of the BatchNorm backward (+ optional column sums of dx through `cs_partial`, >= sm_count * d doubles)
+static int launch_bwd_apply(const float* x, const float* dy, int64_t m, int64_t m_stat, int d, const float* mean, const float* rstd,
+                            const float* gamma, const float* beta, int act, float p_drop, uint64_t seed, uint64_t sid, int batch_stats,
+                            const double* sums, float* dx, double* cs_partial, float* colsum, cudaStream_t st) {
+  const int64_t n8 = m * d / 8;
+  int64_t g = ceil_div(n8, BWA_THREADS);
+  if (g > sm_count()) g = sm_count();
+  if (g < 1) g = 1;
+  k_bn_bwd_apply<<<(unsigned)g, BWA_THREADS, colsum ? BWA_THREADS * 8 * sizeof(double) : 0, st>>>(
+      x, dy, n8, m_stat, d, mean, rstd, gamma, beta, act, p_drop, seed, sid, batch_stats, sums, dx, cs_partial, colsum,
+      colsum ? next_ticket_slot() : 0);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
 #define COL_WS_CHECK(name)                                   \
   if (!ws || ws_bytes < b2g_bn_ws_bytes(d)) {                \
     set_error(name ": workspace too small");                 \
@@ -599,9 +687,8 @@ extern "C" int b2g_bn_bwd_from_sums(const float* x, const float* dy, int64_t m, 
   B2G_CHECK_ARG(m > 0 && m_total >= m && d_ok(d) && x && dy && mean && rstd && gamma && beta && sums && dx, "bn_bwd_from_sums: bad args");
   B2G_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
                 "bn_bwd_from_sums: unaligned pointer");
-  int64_t n8 = m * d / 8;
-  k_bn_bwd_apply<<<ew_grid(n8), 256, 0, st>>>(x, dy, n8, m_total, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, 1, sums, dx);
-  B2G_LAUNCH_CHECK();
+  int rc = launch_bwd_apply(x, dy, m, m_total, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, 1, sums, dx, nullptr, nullptr, st);
+  if (rc != B2G_OK) return rc;
   if (dgamma || dbeta) {
     k_sums_to_float<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(sums, d, dbeta, dgamma);
     B2G_LAUNCH_CHECK();
@@ -629,7 +716,8 @@ extern "C" int b2g_bn_stats_sync(struct b2g_comm* comm, const float* x, int64_t 
 
 extern "C" int b2g_bn_bwd_sync(struct b2g_comm* comm, const float* x, const float* dy, int64_t m, int64_t m_total, int d, const float* mean,
                                const float* rstd, const float* gamma, const float* beta, int relu, float p_drop, uint64_t seed,
-                               uint64_t stream_id, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream_) {
+                               uint64_t stream_id, float* dx, float* dgamma, float* dbeta, float* dx_colsum, void* ws, size_t ws_bytes,
+                               void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(comm && m > 0 && m_total >= m && d_ok(d) && x && dy && mean && rstd && gamma && beta && dx, "bn_bwd_sync: bad args");
   B2G_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
@@ -643,10 +731,7 @@ extern "C" int b2g_bn_bwd_sync(struct b2g_comm* comm, const float* x, const floa
   fin.peer = *reinterpret_cast<const PeerCtx*>(b2g_comm_ctx(comm));
   int rc = launch_col_reduce<1>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, partial, fin, st);
   if (rc != B2G_OK) return rc;
-  int64_t n8 = m * d / 8;
-  k_bn_bwd_apply<<<ew_grid(n8), 256, 0, st>>>(x, dy, n8, m_total, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, 1, sums, dx);
-  B2G_LAUNCH_CHECK();
-  return B2G_OK;
+  return launch_bwd_apply(x, dy, m, m_total, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, 1, sums, dx, partial, dx_colsum, st);
 }
 
 extern "C" int b2g_bn_eval_stats(const float* running_mean, const float* running_var, int d, float eps, float* mean, float* rstd,
@@ -672,7 +757,7 @@ extern "C" int b2g_bn_apply(const float* x, int64_t m, int d, const float* mean,
 
 extern "C" int b2g_bn_bwd(const float* x, const float* dy, int64_t m, int d, const float* mean, const float* rstd, const float* gamma,
                           const float* beta, int relu, float p_drop, uint64_t seed, uint64_t stream_id, int batch_stats, float* dx,
-                          float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream_) {
+                          float* dgamma, float* dbeta, float* dx_colsum, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(m > 0 && d_ok(d) && x && dy && mean && rstd && gamma && beta && dx, "bn_bwd: bad args");
   B2G_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
@@ -684,10 +769,7 @@ extern "C" int b2g_bn_bwd(const float* x, const float* dy, int64_t m, int d, con
   fin.kind = 1; fin.sums = sums; fin.dgamma = dgamma; fin.dbeta = dbeta;
   int rc = launch_col_reduce<1>(x, dy, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, partial, fin, st);
   if (rc != B2G_OK) return rc;
-  int64_t n8 = m * d / 8;
-  k_bn_bwd_apply<<<ew_grid(n8), 256, 0, st>>>(x, dy, n8, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, batch_stats, sums, dx);
-  B2G_LAUNCH_CHECK();
-  return B2G_OK;
+  return launch_bwd_apply(x, dy, m, m, d, mean, rstd, gamma, beta, relu, p_drop, seed, stream_id, batch_stats, sums, dx, partial, dx_colsum, st);
 }
 
 extern "C" int b2g_relu_dropout_fwd(const float* x, int64_t n, int relu, float p_drop, uint64_t seed, uint64_t stream_id, float* y,

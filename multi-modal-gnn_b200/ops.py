@@ -75,6 +75,23 @@ def _run(name, fn, *args):
 
 
 # --------------------------------------------------------------------------------------------------
+# Column sums of a gradient tensor that its PRODUCER already computed (the BatchNorm backward pass writes dx and its
+# column sums in one pass; the nn.Linear in front of the BatchNorm needs exactly those sums as its bias gradient).
+# The hand-over is a tag on the tensor object, valid only while the tensor is unmodified (version counter) -- if autograd
+# accumulated into it or handed over a different tensor, the consumer simply reduces the columns itself.
+# --------------------------------------------------------------------------------------------------
+def _tag_colsum(t: torch.Tensor, colsum: torch.Tensor):
+    t._b2g_colsum = (colsum, t._version, t.data_ptr())
+
+
+def _tagged_colsum(t: torch.Tensor):
+    tag = getattr(t, "_b2g_colsum", None)
+    if tag is None or tag[1] != t._version or tag[2] != t.data_ptr():
+        return None
+    return tag[0]
+
+
+# --------------------------------------------------------------------------------------------------
 # raw (non-differentiable) kernel calls
 # --------------------------------------------------------------------------------------------------
 def linear_fwd_(x, w, b, y, accumulate=False):
@@ -110,6 +127,11 @@ def linear_bwd_weight_(dy, x, dw, db):
     lib = _lib.load()
     m, n = dy.shape
     k = x.shape[1]
+    if db is not None:
+        ready = _tagged_colsum(dy)           # the producer of dy already reduced its columns
+        if ready is not None and ready.shape == db.shape:
+            db.copy_(ready)
+            db = None
     if PRECISION == "tf32" and m >= TC_MIN_ROWS and lib.b2g_linear_bwd_weight_tc_supported(m, n, k) and (db is None or n in (32, 64, 128, 256)):
         ws = workspace(lib.b2g_linear_bwd_weight_tc_ws_bytes(m, n, k), dy.device)
         cost(4 * (m * n + m * k + n * k), 2 * m * n * k)
@@ -290,11 +312,13 @@ class BNActDropFn(Function):
         dx = torch.empty_like(x)
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(beta)
+        colsum = torch.empty(d, dtype=torch.float32, device=x.device)
         ws = workspace(lib.b2g_bn_ws_bytes(d), x.device)
         cost(12 * m * d)
         _run("b2g_bn_bwd", lib.b2g_bn_bwd, x.data_ptr(), dy.data_ptr(), m, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                                   beta.data_ptr(), act, p, seed, sid, int(training), dx.data_ptr(), dgamma.data_ptr(),
-                                  dbeta.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+                                  dbeta.data_ptr(), colsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        _tag_colsum(dx, colsum)
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
@@ -347,10 +371,12 @@ class SyncBNActDropFn(Function):
         inv = 1.0 / dctx.world
         peer = getattr(dctx, "peer", None)
         if peer is not None:      # backward statistics + NVLink exchange fused into the reduction kernel, then dx
-            cost(20 * m * d)
+            colsum = torch.empty(d, dtype=torch.float32, device=dev)
+            cost(12 * m * d)
             _run("b2g_bn_bwd_sync", lib.b2g_bn_bwd_sync, peer.handle, x.data_ptr(), dy.data_ptr(), m, m_total, d, mean.data_ptr(),
                  rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, p, seed, sid, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                 ws.data_ptr(), ws.numel(), _stream())
+                 colsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            _tag_colsum(dx, colsum)
             dctx.count_fused()
             return dx, dgamma * inv, dbeta * inv, None, None, None, None, None, None, None, None, None, None
         sums = torch.empty(2 * d, dtype=torch.float64, device=dev)
@@ -394,7 +420,7 @@ class ActDropFn(Function):
         dx = torch.empty_like(x)
         ws = workspace(lib.b2g_bn_ws_bytes(d), x.device)
         _run("b2g_bn_bwd", lib.b2g_bn_bwd, x.data_ptr(), dy.data_ptr(), m, d, zeros.data_ptr(), ones.data_ptr(), ones.data_ptr(),
-                                  zeros.data_ptr(), act, p, seed, sid, 0, dx.data_ptr(), None, None, ws.data_ptr(),
+                                  zeros.data_ptr(), act, p, seed, sid, 0, dx.data_ptr(), None, None, None, ws.data_ptr(),
                                   ws.numel(), _stream())
         return dx, None, None, None, None, None
 

@@ -860,14 +860,18 @@ def test_peer_comm_single_rank_allreduce_and_fused_batchnorm(dev):
         mean, rstd = a[0], a[1]
 
         def bwd(sync):
-            dx, dg, db = torch.empty_like(x), torch.empty(d, device=dev), torch.empty(d, device=dev)
+            dx, dg, db, cs = torch.empty_like(x), torch.empty(d, device=dev), torch.empty(d, device=dev), torch.empty(d, device=dev)
             if sync:
                 L.check(lib.b2g_bn_bwd_sync(comm, x.data_ptr(), dy.data_ptr(), m, m, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                            beta.data_ptr(), 1, 0.2, 77, 5, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), ws.data_ptr(),
-                                            ws.numel(), None))
+                                            beta.data_ptr(), 1, 0.2, 77, 5, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), cs.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), None))
             else:
                 L.check(lib.b2g_bn_bwd(x.data_ptr(), dy.data_ptr(), m, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                       1, 0.2, 77, 5, 1, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), None))
+                                       1, 0.2, 77, 5, 1, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), cs.data_ptr(), ws.data_ptr(),
+                                       ws.numel(), None))
+            torch.cuda.synchronize()
+            ref = dx.double().sum(0)                       # the fused column sums of dx = the preceding Linear's bias gradient
+            assert float((cs.double() - ref).abs().max()) <= 1e-6 * float(dx.abs().sum(0).max())
             return dx, dg, db
 
         a, b = bwd(False), bwd(True)
