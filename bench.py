@@ -114,6 +114,31 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# C-ABI call -> the kernel that does its work.  Several entry points share one kernel (the tcgen05 linear kernel serves
+# nn.Linear forward, its input gradient and the dense-adjacency products; the tcgen05 MN-major kernel serves weight
+# gradients and the transposed adjacency products): the roofline is reported for the dominant KERNEL.
+KERNEL_OF = {
+    "b2g_linear_fwd_tc": "k_linear_tf32", "b2g_linear_bwd_input_tc": "k_linear_tf32", "b2g_adjacency_mma_fwd": "k_linear_tf32",
+    "b2g_linear_bwd_weight_tc": "k_wgrad_tf32+k_wgrad_tc_reduce", "b2g_adjacency_mma_bwd": "k_wgrad_tf32+k_wgrad_tc_reduce",
+    "b2g_bn_stats": "k_col_reduce<0>", "b2g_col_sums": "k_col_reduce<0>", "b2g_bn_stats_sync": "k_col_reduce<0>",
+    "b2g_bn_local_sums": "k_col_reduce<0>",
+    "b2g_bn_bwd": "k_col_reduce<1>+k_bn_bwd_apply", "b2g_bn_bwd_sync": "k_col_reduce<1>+k_bn_bwd_apply",
+    "b2g_linear_fwd": "k_sgemm_small", "b2g_linear_bwd_input": "k_sgemm_small", "b2g_linear_bwd_weight": "k_sgemm_small",
+    "b2g_decoder_fwd_tc": "k_decoder_fwd_tc", "b2g_decoder_bwd_tc": "k_decoder_bwd_tc", "b2g_bn_apply": "k_bn_apply",
+}
+
+
+def _measured_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r1_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return t.get(kernel)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
@@ -310,12 +335,20 @@ def run_ours(args):
                        "GBps": round(a[2] / a[0] / 1e6, 1) if a[0] > 0 else None,
                        "TFLOPs": round(a[3] / a[0] / 1e9, 2) if a[0] > 0 else None}
                    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])}
-        top = max(agg.items(), key=lambda kv: kv[1][0])
+        fam = {}
+        for k, a in agg.items():
+            f = fam.setdefault(KERNEL_OF.get(k, k), [0.0, 0, 0, 0, []])
+            f[0] += a[0]; f[1] += a[1]; f[2] += a[2]; f[3] += a[3]; f[4].append(k)
+        top = max(fam.items(), key=lambda kv: kv[1][0])
         peaks = _peaks()
-        name, (ms, calls, nbytes, flops) = top[0], top[1]
-        ach = nbytes / calls / (ms / calls * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                "traffic": None, "launches_per_step": calls, "avg_launch_ms": ms / calls, "share_of_step": a_share(ms, tot),
+        name, (ms, calls, nbytes, flops, members) = top[0], top[1]
+        ach = nbytes / calls / (ms / calls * 1e-3) / 1e9          # algorithmic bytes per launch / average launch duration
+        tr = _measured_traffic(name)
+        roof = {"bound": "hbm", "kernel": name, "entry_points": sorted(members), "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": ach / peaks["hbm"], "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
+                "algorithmic_bytes_per_launch": nbytes / calls, "launches_per_step": calls, "avg_launch_ms": ms / calls,
+                "share_of_step": a_share(ms, tot), "tensor_TFLOPs": flops / (ms * 1e-3) / 1e12,
+                "timing": "CUDA events around every library call of one eager (not graph-replayed) step, L2 flushed before the step",
                 "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if peaks["source"] == "measured" else "fallback"}
 
     if world > 1 and dctx.peer is not None:

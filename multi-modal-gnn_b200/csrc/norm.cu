@@ -819,9 +819,10 @@ extern "C" int b2g_l2norm_bwd(const float* y, const float* dy, const float* inv_
   return B2G_OK;
 }
 
+constexpr int LOSS_MAX_PARTS = 2048;     // the reduction is latency-bound (dependent lab -> weight loads): many CTAs in flight
 extern "C" size_t b2g_loss_ws_bytes(int64_t m) {
   (void)m;
-  return align_up((size_t)MAX_PARTIALS * 8, 256) * 2 + 256;
+  return align_up((size_t)LOSS_MAX_PARTS * 8, 256) * 2 + 256;
 }
 
 extern "C" int b2g_weighted_loss(const float* pred, const float* target, const int64_t* lab, const float* w, const uint8_t* sup, int64_t m,
@@ -833,9 +834,10 @@ extern "C" int b2g_weighted_loss(const float* pred, const float* target, const i
     return B2G_EWS;
   }
   double* part_sum = (double*)ws;
-  unsigned long long* part_cnt = (unsigned long long*)((char*)ws + align_up((size_t)MAX_PARTIALS * 8, 256));
+  unsigned long long* part_cnt = (unsigned long long*)((char*)ws + align_up((size_t)LOSS_MAX_PARTS * 8, 256));
   int parts = (int)ceil_div(m > 0 ? m : 1, 256 * 8);
-  if (parts > MAX_PARTIALS) parts = MAX_PARTIALS;
+  const int cap = sm_count() * 8 < LOSS_MAX_PARTS ? sm_count() * 8 : LOSS_MAX_PARTS;
+  if (parts > cap) parts = cap;
   k_loss_partial<<<parts, 256, 0, st>>>(pred, target, lab, w, sup, m, kind, part_sum, part_cnt);
   B2G_LAUNCH_CHECK();
   if (grad && m > 0) {
