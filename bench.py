@@ -320,6 +320,10 @@ def run_ours(args):
     step_device(args.warmup)                     # (every rank runs these two steps: they contain collectives)
     ops.PROFILE = []
     flush.fill_(1)
+    # Park the GPU behind a ~40 ms spin while the host enqueues the whole step: every event pair then brackets kernels
+    # that run back to back, so the per-call durations are device time, not host launch latency (the step is ~270 short
+    # launches; issued into an idle GPU the tiny type-row kernels would be charged ~10 us of launch gap each).
+    torch.cuda._sleep(int(0.040 * 1.9e9))
     step_device(args.warmup)
     torch.cuda.synchronize()
     if rank != 0:
@@ -348,7 +352,7 @@ def run_ours(args):
                 "frac": ach / peaks["hbm"], "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
                 "algorithmic_bytes_per_launch": nbytes / calls, "launches_per_step": calls, "avg_launch_ms": ms / calls,
                 "share_of_step": a_share(ms, tot), "tensor_TFLOPs": flops / (ms * 1e-3) / 1e12,
-                "timing": "CUDA events around every library call of one eager (not graph-replayed) step, L2 flushed before the step",
+                "timing": "CUDA events around every library call of one eager step enqueued behind a 40 ms spin kernel (device time, no launch gaps), L2 flushed before the step",
                 "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if peaks["source"] == "measured" else "fallback"}
 
     if world > 1 and dctx.peer is not None:

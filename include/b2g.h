@@ -234,6 +234,33 @@ int b2g_bn_bwd_sync(b2g_comm_t* comm, const float* x, const float* dy, int64_t m
                     float p_drop, uint64_t seed, uint64_t stream_id, float* dx, float* dgamma, float* dbeta,
                     float* dx_colsum, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (g) optimizer -- torch.optim.Adam(params, lr, weight_decay) as built by train.py:255-260 (betas (0.9, 0.999),
+ *     eps 1e-8, L2 weight decay added to the gradient, no amsgrad) for ALL parameter tensors in one launch
+ *     (SURVEY.md section 8f item 4).  Parameters without a gradient are simply not listed (note N8).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param;          /* [numel] updated in place            */
+  const float* grad;     /* [numel]                             */
+  float* exp_avg;        /* [numel] first moment, in place      */
+  float* exp_avg_sq;     /* [numel] second moment, in place     */
+  int64_t numel;
+} b2g_adam_tensor_t;
+int b2g_adam_chunk_elems(void);
+int b2g_adam_step(const b2g_adam_tensor_t* d_tensors, int n_tensors, const int32_t* d_chunks, int n_chunks,
+                  double step_size, double bc2_sqrt, double one_minus_beta1, double beta2, double one_minus_beta2,
+                  double eps, double weight_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (h) evaluation metrics -- evaluate.py:36-82 (MAE / RMSE / R^2 / MAPE), :88-139 (per lab), :417-440 (per-lab
+ *     +-3 sigma winsorisation of the residuals), one CTA per lab over a by-lab CSR of the pair list
+ *     (SURVEY.md section 8f item 2).  out[n_lab][b2g_eval_fields()] doubles: n, mean residual, residual std,
+ *     number of clipped residuals, sum |r|, sum r^2, sum t, sum t^2, sum |r/t| over t != 0, count of t != 0.
+ * ---------------------------------------------------------------------------------------------- */
+int b2g_eval_fields(void);
+int b2g_eval_per_lab(const float* pred, const float* target, const int32_t* rowptr, const int32_t* pair_of, int n_lab,
+                     int winsorize, float n_sigma, double* out, float* pred_w, void* stream);
+
 /* y = dropout(relu(x)) without normalisation (EdgeRegressionHead, model.py:377-380) and its backward
  * (dx = dy * mask * [y > 0]); in-place allowed. */
 int b2g_relu_dropout_fwd(const float* x, int64_t n, int relu, float p_drop, uint64_t seed, uint64_t stream_id,

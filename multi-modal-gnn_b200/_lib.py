@@ -128,6 +128,11 @@ _PROTOS = {
     "b2g_bn_stats_sync": (c_int, [_P, _P, c_int64, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b2g_bn_bwd_sync": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int, c_float, c_uint64, c_uint64, _P, _P, _P, _P,
                                 _P, c_size_t, _P]),
+    "b2g_adam_chunk_elems": (c_int, []),
+    "b2g_adam_step": (c_int, [_P, c_int, _P, c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                              ctypes.c_double, ctypes.c_double, _P]),
+    "b2g_eval_fields": (c_int, []),
+    "b2g_eval_per_lab": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, _P, _P, _P]),
     "b2g_relu_dropout_fwd": (c_int, [_P, c_int64, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_relu_dropout_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_dropout_mask": (c_int, [c_int64, c_float, c_uint64, c_uint64, _P, _P]),

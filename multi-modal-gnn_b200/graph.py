@@ -213,5 +213,17 @@ class PairIndex:
         self.m = int(patient_idx.numel())
         self.patient_idx = patient_idx.contiguous()
         self.lab_idx = lab_idx.contiguous()
-        self.by_patient = CSR(self.patient_idx, self.patient_idx, n_patient, n_patient, col_is_eid=True)
-        self.by_lab = CSR(self.lab_idx, self.lab_idx, n_lab, n_lab, col_is_eid=True)
+        self.n_patient, self.n_lab = int(n_patient), int(n_lab)
+        self._by_patient = self._by_lab = None       # built on first use: only the decoder's BACKWARD needs them
+
+    @property
+    def by_patient(self) -> "CSR":
+        if self._by_patient is None:
+            self._by_patient = CSR(self.patient_idx, self.patient_idx, self.n_patient, self.n_patient, col_is_eid=True)
+        return self._by_patient
+
+    @property
+    def by_lab(self) -> "CSR":
+        if self._by_lab is None:
+            self._by_lab = CSR(self.lab_idx, self.lab_idx, self.n_lab, self.n_lab, col_is_eid=True)
+        return self._by_lab

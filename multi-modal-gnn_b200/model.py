@@ -199,6 +199,8 @@ class HeteroRGCN(nn.Module):
         self._pair_plans: "OrderedDict[int, _PairPlan]" = OrderedDict()
         self._last_streams: Optional[_DropoutStreams] = None
         self._seed_buffer: Optional[torch.Tensor] = None      # set by Trainer.enable_cuda_graph()
+        self._embedding_cache_on = False                      # enable_embedding_cache(): eval-mode (init, x) reuse
+        self._embedding_cache = None
         self.dist: Optional[DistContext] = None               # set by set_distributed(): patient-partitioned multi-GPU
         self._register_load_state_dict_pre_hook(self._rename_pyg24_keys)
         logging.info(f"Initialized HeteroRGCN with hidden_dim={hidden_dim}, num_layers={num_layers}")
@@ -326,6 +328,70 @@ class HeteroRGCN(nn.Module):
             globalize_degrees(gi, self.dist)       # mean onto replicated types divides by the global neighbour count
         return gi
 
+    # ------------------------------------------------------------------------------------------
+    # inference: the reference's per-patient report calls predict_lab_values twice per patient and every call recomputes
+    # the full-graph forward (inference.py:92-159).  In eval mode without autograd the node embeddings only depend on
+    # the graph and the parameters, so they can be kept.
+    def enable_embedding_cache(self, enabled: bool = True):
+        """Opt-in: in eval mode under torch.no_grad(), keep the pre-GNN and post-GNN node embeddings of the last graph and
+        reuse them while no parameter or buffer has been modified (checked through the tensors' version counters)."""
+        self._embedding_cache_on = bool(enabled)
+        self._embedding_cache = None
+
+    def _state_versions(self):
+        return tuple(t._version for t in self.parameters()) + tuple(t._version for t in self.buffers())
+
+    def _eval_embeddings(self, data, gi: GraphIndex, node_types, streams):
+        """(init, x) for eval mode: model.py:294 and :301 (one encode serves both, as dropout is off)."""
+        use = self._embedding_cache_on and not torch.is_grad_enabled()
+        key = (id(gi), self._state_versions()) if use else None
+        if use and self._embedding_cache is not None and self._embedding_cache[0] == key and self._embedding_cache[1] is gi:
+            return self._embedding_cache[2], self._embedding_cache[3]
+        init = self._encode(node_types, streams, "enc")
+        x = self._gnn(init, gi, streams)
+        if use:
+            self._embedding_cache = (key, gi, init, x)
+        return init, x
+
+    @torch.no_grad()
+    def impute_missing(self, data, patient_ids: Optional[torch.Tensor] = None, chunk_pairs: int = 1 << 24):
+        """All never-measured (patient, lab) pairs of the given patients (default: every patient) and their predicted
+        normalised values -- the bulk form of inference.py:140-159 ("truly missing labs"), which the reference runs one
+        patient at a time.  Returns (patient_idx int64[K], lab_idx int64[K], prediction float32[K]), ordered by patient,
+        then lab.  Eval mode only; the node embeddings are computed once."""
+        if self.training:
+            raise _lib.B2GError("impute_missing runs in eval mode (call model.eval() first)")
+        self._check_device()
+        if len(self.embeddings) == 0:
+            self._init_embeddings(data)
+        gi = self._graph_index(data)
+        dev = self._device()
+        n_p, n_l = gi.node_counts["patient"], gi.node_counts["lab"]
+        rel = gi.relations.get(("patient", "has_lab", "lab"))
+        if rel is None:
+            raise _lib.B2GError("graph has no ('patient','has_lab','lab') relation")
+        ids = torch.arange(n_p, device=dev) if patient_ids is None else patient_ids.to(dev).long().unique()
+        was_on, self._embedding_cache_on = self._embedding_cache_on, True
+        try:
+            out_p, out_l, out_v = [], [], []
+            rows_per_chunk = max(1, chunk_pairs // max(n_l, 1))
+            rowptr, col = rel.by_src.rowptr.long(), rel.by_src.col.long()          # by patient: measured labs of each patient
+            for s0 in range(0, int(ids.numel()), rows_per_chunk):
+                sub = ids[s0:s0 + rows_per_chunk]
+                measured = torch.zeros((sub.numel(), n_l), dtype=torch.bool, device=dev)
+                beg, cnt = rowptr[sub], rowptr[sub + 1] - rowptr[sub]
+                row_of = torch.repeat_interleave(torch.arange(sub.numel(), device=dev), cnt)
+                pos = torch.arange(int(cnt.sum()), device=dev) - torch.repeat_interleave(cnt.cumsum(0) - cnt, cnt) + torch.repeat_interleave(beg, cnt)
+                measured[row_of, col[pos]] = True
+                miss = (~measured).nonzero()
+                pi, li = sub[miss[:, 0]].contiguous(), miss[:, 1].contiguous()
+                out_p.append(pi)
+                out_l.append(li)
+                out_v.append(self.predict_lab_values(data, pi, li) if pi.numel() else torch.zeros(0, device=dev))
+            return torch.cat(out_p), torch.cat(out_l), torch.cat(out_v)
+        finally:
+            self._embedding_cache_on = was_on
+
     def _check_device(self):
         if self._device().type != "cuda":
             raise _lib.B2GError("HeteroRGCN runs only on a CUDA device (B200); call .to('cuda') first -- there is no CPU path")
@@ -363,6 +429,9 @@ class HeteroRGCN(nn.Module):
         if training and self.dropout > 0:
             init = self._encode(node_types, streams, "init.enc")         # model.py:294
             x0 = self._encode(node_types, streams, "fwd.enc")            # model.py:251 (fresh masks, N3)
+        elif not training:
+            init, x = self._eval_embeddings(data, gi, node_types, streams)
+            x0 = None
         else:
             bns = [self.patient_transform[1], self.patient_transform[5]]
             before = [(b.running_mean.clone(), b.running_var.clone()) for b in bns] if training else None
@@ -376,7 +445,8 @@ class HeteroRGCN(nn.Module):
                         b.running_mean.mul_(2 - mom).sub_(rm0, alpha=1 - mom)
                         b.running_var.mul_(2 - mom).sub_(rv0, alpha=1 - mom)
                         b.num_batches_tracked += 1
-        x = self._gnn(x0, gi, streams)
+        if x0 is not None:
+            x = self._gnn(x0, gi, streams)
 
         plan = self._pair_plan(gi, patient_indices, lab_indices)
         if self.dist is not None:

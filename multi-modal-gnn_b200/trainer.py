@@ -137,8 +137,9 @@ class Trainer:
 
     def _build_optimizer(self, oc):
         kind = oc.get("type", "adam").lower()
-        if kind == "adam":
-            return torch.optim.Adam(self.model.parameters(), lr=oc["lr"], weight_decay=oc["weight_decay"])
+        if kind == "adam":          # train.py:255-260; one-launch multi-tensor step (optim.py) instead of torch's foreach kernels
+            from .optim import FusedAdam
+            return FusedAdam(self.model.parameters(), lr=oc["lr"], weight_decay=oc["weight_decay"])
         if kind == "sgd":
             return torch.optim.SGD(self.model.parameters(), lr=oc["lr"], weight_decay=oc["weight_decay"],
                                    momentum=oc.get("momentum", 0.9))

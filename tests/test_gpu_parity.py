@@ -880,3 +880,151 @@ def test_peer_comm_single_rank_allreduce_and_fused_batchnorm(dev):
         assert lib.b2g_comm_error(comm) == 0
     finally:
         L.check(lib.b2g_comm_destroy(comm))
+
+
+# ------------------------------------------------------------------------------------------------------
+# (g) one-launch Adam == torch.optim.Adam (train.py:255-260), including skipped (grad is None) parameters,
+#     a parameter that starts receiving gradients later, and state_dict exchange in both directions
+# ------------------------------------------------------------------------------------------------------
+def test_fused_adam_matches_torch_adam(dev):
+    O = importlib.import_module(PKG + ".optim")
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(128, 128), (128,), (64, 256), (1, 32), (1,), (4099,), (460, 128), (7, 3)]
+    mine = [torch.randn(*s, generator=gen).to(dev).requires_grad_(True) for s in shapes]
+    ref = [p.detach().clone().requires_grad_(True) for p in mine]
+    a, b = O.FusedAdam(mine, lr=1e-3, weight_decay=1e-5), torch.optim.Adam(ref, lr=1e-3, weight_decay=1e-5)
+    for step in range(6):
+        for i, (p, q) in enumerate(zip(mine, ref)):
+            if i == 3 or (i == 5 and step < 2):       # never / late gradients
+                p.grad = q.grad = None
+                continue
+            g = torch.randn(*shapes[i], generator=gen).to(dev) * (10.0 ** (i - 4))
+            p.grad, q.grad = g.clone(), g.clone()
+        if step == 3:
+            b.param_groups[0]["lr"] = a.param_groups[0]["lr"] = 5e-4          # what ReduceLROnPlateau does
+        a.step()
+        b.step()
+    assert a.launches == 6 + 4                        # one launch per step, plus one for the late cohort
+    for i, (p, q) in enumerate(zip(mine, ref)):
+        assert relerr(p, q) <= 2e-6, (i, relerr(p, q))
+        if i == 3:
+            assert len(a.state[p]) == 0 and len(b.state[q]) == 0
+        else:
+            assert float(a.state[p]["step"]) == float(b.state[q]["step"])
+            assert relerr(a.state[p]["exp_avg"], b.state[q]["exp_avg"]) <= 2e-6
+            assert relerr(a.state[p]["exp_avg_sq"], b.state[q]["exp_avg_sq"]) <= 2e-6
+    # checkpoints move between the two implementations
+    b2 = torch.optim.Adam(ref, lr=1e-3, weight_decay=1e-5)
+    b2.load_state_dict(a.state_dict())
+    a2 = O.FusedAdam(mine, lr=1e-3, weight_decay=1e-5)
+    a2.load_state_dict(b.state_dict())
+    for p, q in zip(mine, ref):
+        if p.grad is not None:
+            g = torch.randn(p.shape, generator=gen).to(dev)
+            p.grad, q.grad = g.clone(), g.clone()
+    a2.step()
+    b2.step()
+    for i, (p, q) in enumerate(zip(mine, ref)):
+        assert relerr(p, q) <= 1e-5, (i, relerr(p, q))      # the two runs entered this step 2e-6 apart
+
+
+# ------------------------------------------------------------------------------------------------------
+# inference: eval-mode embedding cache (inference.py:92-159 calls predict_lab_values per patient) and the bulk
+# "all never-measured pairs" imputer (inference.py:140-159), against the reference's own eval-mode predictions
+# ------------------------------------------------------------------------------------------------------
+def test_embedding_cache_and_bulk_imputation(golden_tiny_mae, dev):
+    pkg, G, ops, M, T, L = _mods()
+    blob = golden_tiny_mae
+    state = dict(blob["state_before"])
+    state.update(blob["after_buffers"])
+    model, g, counts, ets, eid, attr = _model_from_golden(blob, dev, dropout=0.2, state=state)
+    model.eval()
+    ei = eid[("patient", "has_lab", "lab")]
+    pi, li = ei[0].to(dev), ei[1].to(dev)
+    lib = L.load()
+    with torch.no_grad():
+        plain = model.predict_lab_values(g, pi, li)
+        model.enable_embedding_cache()
+        lib.b2g_reset_launch_count()
+        first = model.predict_lab_values(g, pi, li)
+        n_first = lib.b2g_launch_count()
+        lib.b2g_reset_launch_count()
+        second = model.predict_lab_values(g, pi, li)
+        n_second = lib.b2g_launch_count()
+        assert torch.equal(plain, first) and torch.equal(first, second)
+        assert n_second < n_first / 4                     # only the decoder ran the second time
+        assert relerr(second, blob["pred_all"]) <= 5e-5   # == the unmodified reference's eval-mode predictions
+        # a modified parameter invalidates the cache
+        model.edge_predictor.mlp[0].bias.add_(0.25)
+        third = model.predict_lab_values(g, pi, li)
+        model.enable_embedding_cache(False)
+        fresh = model.predict_lab_values(g, pi, li)
+        assert torch.equal(third, fresh) and not torch.equal(third, second)
+        model.edge_predictor.mlp[0].bias.sub_(0.25)
+        # training mode never uses the cache
+        model.enable_embedding_cache()
+        model.train()
+        with torch.enable_grad():
+            model.predict_lab_values(g, pi, li).sum().backward()
+        model.eval()
+
+        # bulk imputation of every never-measured pair of a patient subset, and of all patients
+        n_p, n_l = counts["patient"], counts["lab"]
+        have = set(zip(ei[0].tolist(), ei[1].tolist()))
+        some = torch.tensor([0, 5, 17, 17, n_p - 1])
+        mp, ml, mv = model.impute_missing(g, some)
+        want = [(p, l) for p in sorted(set(some.tolist())) for l in range(n_l) if (p, l) not in have]
+        assert list(zip(mp.tolist(), ml.tolist())) == want
+        assert torch.equal(mv, model.predict_lab_values(g, mp, ml))
+        ap, al, av = model.impute_missing(g, chunk_pairs=1000)        # several chunks
+        assert ap.numel() == n_p * n_l - len(have) and av.shape == ap.shape and bool(torch.isfinite(av).all())
+        # against the CPU oracle on the same pairs
+        sd = {k: v.cpu() for k, v in model.state_dict().items()}
+        ref = R.predict_lab_values(sd, counts, ets, eid, mp.cpu(), ml.cpu(), False)
+        assert relerr(mv, ref) <= 5e-5
+    with pytest.raises(L.B2GError):
+        model.train()
+        model.impute_missing(g, some)
+
+
+# ------------------------------------------------------------------------------------------------------
+# (h) on-device evaluation metrics == the reference's evaluate.py functions (golden) and the numpy oracle
+# ------------------------------------------------------------------------------------------------------
+def test_eval_metrics_match_reference(dev):
+    import math
+    import os
+    from oracle import eval_metrics_ref as E
+    MX = importlib.import_module(PKG + ".metrics")
+    blob = torch.load(os.path.join(os.path.dirname(__file__), "golden", "eval_metrics.pt"), weights_only=False)
+    p, t, lab = blob["pred"].to(dev), blob["target"].to(dev), blob["lab"].to(dev)
+
+    def close(a, b, tol=1e-5):
+        return (math.isnan(a) and math.isnan(b)) or abs(a - b) <= tol * max(1.0, abs(b))
+
+    for tag, wins in (("raw", False), ("winsorized", True)):
+        res = MX.evaluate_predictions(p, t, lab, blob["n_labs"], winsorize=wins, return_winsorized=True)
+        want = blob[f"overall_{tag}"]
+        assert all(close(res["overall"][k], want[k]) for k in ("mae", "rmse", "r2", "mape")), (tag, res["overall"], want)
+        wrows = {r["lab_index"]: r for r in blob[f"per_lab_{tag}"]}
+        assert sorted(r["lab_index"] for r in res["per_lab"]) == sorted(wrows)
+        maes = [r["mae"] for r in res["per_lab"]]
+        assert maes == sorted(maes)
+        for r in res["per_lab"]:
+            w = wrows[r["lab_index"]]
+            assert r["num_samples"] == w["num_samples"]
+            assert all(close(r[k], w[k]) for k in ("mae", "rmse", "r2", "mape")), (tag, r, w)
+        if wins:
+            # the cap bounds come from fp64 moments here and float32 moments in numpy: a residual that sits on a bound may
+            # be counted differently, the capped VALUES agree to float32 rounding
+            assert abs(res["num_capped"] - blob["num_capped"]) <= 3
+            assert float((res["predictions"].cpu() - blob["pred_winsorized"]).abs().max()) <= 2e-5
+        else:
+            assert res["num_capped"] == 0 and torch.equal(res["predictions"], p)
+    # run-to-run identical (fixed-order reductions)
+    a = MX.evaluate_predictions(p, t, lab, blob["n_labs"])["records"]
+    b = MX.evaluate_predictions(p, t, lab, blob["n_labs"])["records"]
+    assert torch.equal(a, b)
+    # degenerate inputs: no pairs at all
+    e = torch.zeros(0, device=dev)
+    res = MX.evaluate_predictions(e, e, torch.zeros(0, dtype=torch.int64, device=dev), 5)
+    assert res["per_lab"] == [] and math.isnan(res["overall"]["mae"])

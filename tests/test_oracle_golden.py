@@ -98,3 +98,32 @@ def test_regression_loss_variants():
     assert abs(float(R.regression_loss(p, t, "huber")) - float(torch.nn.functional.huber_loss(p, t))) < 1e-6
     with pytest.raises(ValueError):
         R.regression_loss(p, t, "nope")
+
+
+def test_eval_metrics_restatement_matches_reference_functions():
+    """oracle/eval_metrics_ref.py against what the unmodified reference's compute_regression_metrics /
+    compute_per_lab_metrics (evaluate.py:36-139) returned on the seeded case (tests/golden/eval_metrics.pt)."""
+    import math
+    import os
+    import numpy as np
+    import torch
+    from oracle import eval_metrics_ref as E
+    blob = torch.load(os.path.join(os.path.dirname(__file__), "golden", "eval_metrics.pt"), weights_only=False)
+    p, t, lab = blob["pred"].numpy(), blob["target"].numpy(), blob["lab"].numpy()
+    p2, t2, lab2 = E.synthetic_case()
+    assert np.array_equal(p, p2) and np.array_equal(t, t2) and np.array_equal(lab, lab2)      # the case is reproducible
+    pw, n_cap = E.winsorize(p, t, lab)
+    assert n_cap == blob["num_capped"] and np.array_equal(pw, blob["pred_winsorized"].numpy())
+
+    def close(a, b):
+        return (math.isnan(a) and math.isnan(b)) or abs(a - b) <= 2e-6 * max(1.0, abs(b))
+
+    for tag, pp in (("raw", p), ("winsorized", pw)):
+        got, want = E.regression_metrics(pp, t), blob[f"overall_{tag}"]
+        assert all(close(got[k], want[k]) for k in ("mae", "rmse", "r2", "mape")), (tag, got, want)
+        rows, wrows = E.per_lab_metrics(pp, t, lab), blob[f"per_lab_{tag}"]
+        assert [r["lab_index"] for r in rows] == [r["lab_index"] for r in wrows]               # same labs, same MAE order
+        for r, w in zip(rows, wrows):
+            assert r["num_samples"] == w["num_samples"]
+            assert all(close(r[k], w[k]) for k in ("mae", "rmse", "r2", "mape")), (tag, r, w)
+    assert 48 not in [r["lab_index"] for r in rows] and 49 not in [r["lab_index"] for r in rows]   # 1-sample / empty labs

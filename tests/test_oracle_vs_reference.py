@@ -86,3 +86,23 @@ def test_ten_training_steps_track_reference(pkg):
         ref_pred = model.predict_lab_values(d, ei[0], ei[1])
         pred = R.predict_lab_values({k: v.detach() for k, v in sd.items()}, counts, ets, eid, ei[0], ei[1], False)
     torch.testing.assert_close(pred, ref_pred, rtol=1e-3, atol=1e-4)
+
+
+def test_eval_metrics_restatement_vs_live_reference():
+    """oracle/eval_metrics_ref.py against the reference's evaluate.py functions imported unmodified, on fresh seeds."""
+    import importlib
+    import math
+    from oracle import eval_metrics_ref as E
+    H.load_reference()
+    ev = importlib.import_module("evaluate")
+    assert ev.__file__.startswith("/root/reference/src")
+    for seed in (1, 2, 3):
+        p, t, lab = E.synthetic_case(seed=seed, n_pairs=5000, n_labs=20)
+        pw, _ = E.winsorize(p, t, lab)
+        for pp in (p, pw):
+            got, want = E.regression_metrics(pp, t), ev.compute_regression_metrics(pp, t)
+            for k in ("mae", "rmse", "r2", "mape"):
+                assert (math.isnan(got[k]) and math.isnan(want[k])) or abs(got[k] - want[k]) <= 2e-6 * max(1.0, abs(want[k])), (seed, k)
+            rows, df = E.per_lab_metrics(pp, t, lab), ev.compute_per_lab_metrics(pp, t, lab, {})
+            assert [r["lab_index"] for r in rows] == df["lab_index"].tolist()
+            assert [r["num_samples"] for r in rows] == df["num_samples"].tolist()
