@@ -44,12 +44,13 @@ def evaluate_predictions(predictions: torch.Tensor, targets: torch.Tensor, lab_i
     lab = lab_indices.contiguous().long()
     if not (pred.numel() == tgt.numel() == lab.numel()):
         raise ValueError("predictions, targets and lab_indices must have the same length")
-    by_lab = CSR(lab, lab, int(num_labs), int(num_labs), col_is_eid=True)          # pairs of each lab, original order
-    rec = torch.empty((int(num_labs), len(FIELDS)), dtype=torch.float64, device=pred.device)
+    rec = torch.zeros((int(num_labs), len(FIELDS)), dtype=torch.float64, device=pred.device)
     pw: Optional[torch.Tensor] = torch.empty_like(pred) if return_winsorized else None
-    _lib.check(lib.b2g_eval_per_lab(pred.data_ptr(), tgt.data_ptr(), by_lab.rowptr.data_ptr(), by_lab.col.data_ptr(), int(num_labs),
+    if pred.numel() > 0:
+        by_lab = CSR(lab, lab, int(num_labs), int(num_labs), col_is_eid=True)      # pairs of each lab, original order
+        _lib.check(lib.b2g_eval_per_lab(pred.data_ptr(), tgt.data_ptr(), by_lab.rowptr.data_ptr(), by_lab.col.data_ptr(), int(num_labs),
                                     int(bool(winsorize)), float(n_sigma), rec.data_ptr(), None if pw is None else pw.data_ptr(), _stream()),
-               "b2g_eval_per_lab")
+                   "b2g_eval_per_lab")
     host = rec.cpu()
     tot = host.sum(0).tolist()
     out: Dict[str, object] = {"overall": _metrics_from_sums(tot[0], tot[4], tot[5], tot[6], tot[7], tot[8], tot[9]),

@@ -90,6 +90,15 @@ class FusedAdam(torch.optim.Optimizer):
                 self.launches += 1
         return loss
 
+    def state_dict(self):
+        """torch.optim.Adam's layout.  The step counters are shared between parameters internally; every parameter gets
+        its own copy here, because torch's foreach Adam increments each listed step tensor once per parameter."""
+        sd = super().state_dict()
+        for st in sd["state"].values():
+            if "step" in st:
+                st["step"] = st["step"].clone()
+        return sd
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._tables.clear()
