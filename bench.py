@@ -225,7 +225,8 @@ def run_ours(args):
     # compute on the union graph (checked by tools/dist_check.py), plus one flat gradient all-reduce per step.
     D = importlib.import_module(PKG + ".dist")
     dctx = D.DistContext(device=dev) if world > 1 else None
-    g_host = pkg.synth.make_graph(spec, seed=42 + rank)
+    # the large configs are drawn on the GPU (the CPU generator needs minutes at >= 1 M patients); C1 / C2 on the host
+    g_host = pkg.synth.make_graph(spec, seed=42 + rank, device=dev if spec.n_patient >= 500_000 else "cpu")
     masker = T.EdgeMasker(g_host, 0.7, 0.15, 0.15, 0.2, 42 + rank)
     torch.manual_seed(0)
     model = M.build_model(cfg, (g_host.node_types, g_host.edge_types), None)

@@ -57,6 +57,8 @@ SPECS = {
     "C2": GraphSpec("C2", 46520, 160, 200, 100, 5_000_000, 441_000, 1_296_000, low_degree_frac=0.01),
     "C3": GraphSpec("C3", 1_000_000, 50, 200, 100, 20_000_000, 1_764_000, 5_182_000, low_degree_frac=0.12),
     "C4": GraphSpec("C4", 10_000_000, 50, 200, 100, 100_000_000, 8_820_000, 25_910_000, low_degree_frac=0.12),
+    # one rank's share of C4 when its 10 M patients are partitioned over 8 GPUs (bench.py --workload C4s8 --gpus 8 == C4)
+    "C4s8": GraphSpec("C4s8", 1_250_000, 50, 200, 100, 12_500_000, 1_102_500, 3_238_750, low_degree_frac=0.12),
     "C5": GraphSpec("C5", 10_000_000, 50, 200, 100, 100_000_000, 8_820_000, 25_910_000,
                     low_degree_frac=0.12, hidden_dim=256),
 }
