@@ -132,6 +132,21 @@ int b2g_gather_values(const float* src, const int64_t* idx, int64_t m, float* ou
 /* ------------------------------------------------------------------------------------------------
  * (d) dense layers -- nn.Linear / SAGEConv.lin_l / lin_r / EdgeRegressionHead (model.py:93-103,373-386)
  * ---------------------------------------------------------------------------------------------- */
+/* Grouped small GEMMs: the type-node side of a HeteroConv layer (lab / diagnosis / medication rows: three relations x
+ * {lin_l on the sources, lin_r on the destinations, lin_l on the aggregates}, forward and backward) is ~50 launches of
+ * <= 200-row problems per step; one launch takes up to 12 of them.  C[m,n] = (accumulate ? C : 0) + opA(a) opB(b)
+ * (+ opA(a2) opB(b2)) + bias.  a_transposed: a is stored [k, m]; b_is_nk: b is stored [n, k] (nn.Linear weight). */
+typedef struct {
+  const float* a;  const float* b;      /* first product, reduction length k                       */
+  const float* a2; const float* b2;     /* optional second product into the same C, length k2      */
+  const float* bias;                    /* [n] or NULL                                             */
+  float* c;                             /* [m, n]                                                  */
+  int32_t m, n, k, k2;
+  int32_t a_transposed, b_is_nk, accumulate, reserved;
+} b2g_gemm_problem_t;
+int b2g_small_gemm_group(const b2g_gemm_problem_t* h_probs, int n_probs, void* stream);
+int b2g_small_colsum_group(const float* const* h_x, float* const* h_out, const int* h_m, const int* h_n, int count,
+                           void* stream);
 /* y[M,N] = (accumulate ? y : 0) + x[M,K] * w[N,K]^T + bias[N]   (bias may be NULL)  fp32 SIMT */
 int b2g_linear_fwd(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y,
                    int accumulate, void* stream);

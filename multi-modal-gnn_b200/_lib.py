@@ -29,6 +29,14 @@ class RelT(ctypes.Structure):
                 ("col_scale", c_void_p)]
 
 
+class GemmProblemT(ctypes.Structure):
+    """b2g_gemm_problem_t"""
+    _fields_ = [("a", c_void_p), ("b", c_void_p), ("a2", c_void_p), ("b2", c_void_p), ("bias", c_void_p), ("c", c_void_p),
+                ("m", ctypes.c_int32), ("n", ctypes.c_int32), ("k", ctypes.c_int32), ("k2", ctypes.c_int32),
+                ("a_transposed", ctypes.c_int32), ("b_is_nk", ctypes.c_int32), ("accumulate", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
 def _sources():
     extra = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu") and f not in SOURCES)
     return SOURCES + extra
@@ -133,6 +141,9 @@ _PROTOS = {
                               ctypes.c_double, ctypes.c_double, _P]),
     "b2g_eval_fields": (c_int, []),
     "b2g_eval_per_lab": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, _P, _P, _P]),
+    "b2g_small_gemm_group": (c_int, [ctypes.POINTER(GemmProblemT), c_int, _P]),
+    "b2g_small_colsum_group": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                       c_int, _P]),
     "b2g_relu_dropout_fwd": (c_int, [_P, c_int64, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_relu_dropout_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_dropout_mask": (c_int, [c_int64, c_float, c_uint64, c_uint64, _P, _P]),

@@ -195,6 +195,127 @@ __global__ void __launch_bounds__(256) k_sgemm_small(const float* __restrict__ A
 }
 constexpr int SMALL_M = 1024;
 
+// ---- grouped small problems ---------------------------------------------------------------------------------------------
+// The type-node side of a HeteroConv layer is a swarm of tiny GEMMs (<= a few hundred rows, K = N = 128): three relations
+// x {lin_l on the sources, lin_r on the destinations, lin_l on the aggregates} forward, and twice that backward -- ~50
+// launches of ~5 us per step.  One launch takes a list of independent problems
+//      C[M,N] = (acc ? C : 0) + opA(A) opB(B) (+ opA(A2) opB(B2)) + bias        (the optional second product shares C)
+// and spreads their 32 x 32 tiles over one grid.  Same tile code and operand conventions as k_sgemm_small (A_T / B_NK
+// are per-problem flags here), so each problem's result is bit-identical to the single-problem kernel's.
+constexpr int GROUP_MAX = 12;
+struct GroupPack {
+  b2g_gemm_problem_t p[GROUP_MAX];
+  int tile_begin[GROUP_MAX + 1];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) k_sgemm_group(GroupPack g) {
+  constexpr int KT = 128;
+  __shared__ float As[KT][33];     // [k][m]
+  __shared__ float Bs[KT][33];     // [k][n]
+  int pi = 0;
+  while (pi + 1 < g.n && (int)blockIdx.x >= g.tile_begin[pi + 1]) ++pi;
+  const b2g_gemm_problem_t& P = g.p[pi];
+  const int M = P.m, N = P.n;
+  const int tiles_n = (N + 31) / 32;
+  const int t = blockIdx.x - g.tile_begin[pi];
+  const int m0 = (t / tiles_n) * 32, n0 = (t % tiles_n) * 32;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lr = tid >> 3, lq = (tid & 7) * 4;
+  const bool A_T = P.a_transposed != 0, B_NK = P.b_is_nk != 0;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int src = 0; src < 2; ++src) {
+    const float* __restrict__ Ap = src == 0 ? P.a : P.a2;
+    const float* __restrict__ Bp = src == 0 ? P.b : P.b2;
+    const int K = src == 0 ? P.k : P.k2;
+    if (Ap == nullptr || K <= 0) continue;
+    for (int k0 = 0; k0 < K; k0 += KT) {
+      float ra[16], rb[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (A_T) {
+            int k = k0 + lr + 32 * j, m = m0 + lq + q;
+            ra[4 * j + q] = (k < K && m < M) ? __ldg(Ap + (size_t)k * M + m) : 0.f;
+          } else {
+            int m = m0 + lr, k = k0 + lq + q + 32 * j;
+            ra[4 * j + q] = (m < M && k < K) ? __ldg(Ap + (size_t)m * K + k) : 0.f;
+          }
+          if (B_NK) {
+            int n = n0 + lr, k = k0 + lq + q + 32 * j;
+            rb[4 * j + q] = (n < N && k < K) ? __ldg(Bp + (size_t)n * K + k) : 0.f;
+          } else {
+            int k = k0 + lr + 32 * j, n = n0 + lq + q;
+            rb[4 * j + q] = (k < K && n < N) ? __ldg(Bp + (size_t)k * N + n) : 0.f;
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (A_T) As[lr + 32 * j][lq + q] = ra[4 * j + q]; else As[lq + q + 32 * j][lr] = ra[4 * j + q];
+          if (B_NK) Bs[lq + q + 32 * j][lr] = rb[4 * j + q]; else Bs[lr + 32 * j][lq + q] = rb[4 * j + q];
+        }
+      }
+      __syncthreads();
+      const int kmax = min(KT, K - k0);
+#pragma unroll 8
+      for (int k = 0; k < kmax; ++k) {
+        float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
+        float b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+        acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+        acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int m = m0 + ty * 2 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      int n = n0 + tx * 2 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (P.bias ? __ldg(P.bias + n) : 0.f);
+      float* dst = P.c + (size_t)m * N + n;
+      *dst = P.accumulate ? *dst + v : v;
+    }
+  }
+}
+
+// column sums of several small matrices in one launch (bias gradients of the grouped problems): 32 columns per CTA
+struct ColsumPack {
+  const float* x[GROUP_MAX];
+  float* out[GROUP_MAX];
+  int m[GROUP_MAX], n[GROUP_MAX];
+  int cta_begin[GROUP_MAX + 1];
+  int count;
+};
+__global__ void __launch_bounds__(256) k_colsum_group(ColsumPack g) {
+  __shared__ float sh[8][32];
+  int pi = 0;
+  while (pi + 1 < g.count && (int)blockIdx.x >= g.cta_begin[pi + 1]) ++pi;
+  const float* __restrict__ dy = g.x[pi];
+  const int M = g.m[pi], N = g.n[pi];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int n = (blockIdx.x - g.cta_begin[pi]) * 32 + lane;
+  float s = 0.f;
+  if (n < N) {
+#pragma unroll 8
+    for (int m = slice; m < M; m += 8) s += __ldg(dy + (size_t)m * N + n);
+  }
+  sh[slice][lane] = s;
+  __syncthreads();
+  if (slice != 0 || n >= N) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) s += sh[k][lane];
+  g.out[pi][n] = s;
+}
+
+
 // db[n] = sum_m dy[m, n] for a few hundred rows: 32 columns per CTA, 8 row slices (one per warp, coalesced 128-byte row
 // segments, 8 loads in flight), slices combined in fixed order: deterministic
 __global__ void __launch_bounds__(256) k_colsum_small(const float* __restrict__ dy, int M, int N, float* __restrict__ db) {
@@ -374,5 +495,53 @@ extern "C" int b2g_linear_bwd_weight(const float* dy, const float* x, int64_t m,
     k_wgrad_reduce<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(part_b, slices, n, db);
     B2G_LAUNCH_CHECK();
   }
+  return B2G_OK;
+}
+
+
+/* Up to 12 independent small problems C = (acc ? C : 0) + opA(A) opB(B) (+ opA(A2) opB(B2)) + bias in ONE launch
+ * (h_probs is a HOST array; every m <= 1024).  Operand conventions of b2g_gemm_problem_t are those of the three small
+ * linear entry points: forward (a = x [m,k], b = W [n,k], b_is_nk = 1), input gradient (a = dy [m,k], b = W [k,n],
+ * b_is_nk = 0), weight gradient (a = dy stored [k,m], a_transposed = 1, b = x [k,n], b_is_nk = 0). */
+extern "C" int b2g_small_gemm_group(const b2g_gemm_problem_t* h_probs, int n_probs, void* stream_) {
+  B2G_CHECK_ARG(n_probs >= 0 && n_probs <= GROUP_MAX && (n_probs == 0 || h_probs), "small_gemm_group: at most %d problems", GROUP_MAX);
+  GroupPack g{};
+  int tiles = 0, cnt = 0;
+  for (int i = 0; i < n_probs; ++i) {
+    const b2g_gemm_problem_t& P = h_probs[i];
+    B2G_CHECK_ARG(P.m >= 0 && P.n > 0 && P.k > 0 && P.m <= SMALL_M && P.c && P.a && P.b && (P.a2 == nullptr || (P.b2 && P.k2 > 0)),
+                  "small_gemm_group: bad problem %d (m=%d n=%d k=%d)", i, P.m, P.n, P.k);
+    if (P.m == 0) continue;
+    g.p[cnt] = P;
+    g.tile_begin[cnt] = tiles;
+    tiles += (int)(ceil_div(P.m, 32) * ceil_div(P.n, 32));
+    ++cnt;
+  }
+  g.tile_begin[cnt] = tiles;
+  g.n = cnt;
+  if (tiles == 0) return B2G_OK;
+  k_sgemm_group<<<(unsigned)tiles, 256, 0, (cudaStream_t)stream_>>>(g);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+/* out_i[n] = sum_m x_i[m, n] for up to 12 small matrices (m <= 1024) in one launch; h_* are HOST arrays. */
+extern "C" int b2g_small_colsum_group(const float* const* h_x, float* const* h_out, const int* h_m, const int* h_n, int count,
+                                      void* stream_) {
+  B2G_CHECK_ARG(count >= 0 && count <= GROUP_MAX && (count == 0 || (h_x && h_out && h_m && h_n)), "small_colsum_group: bad args");
+  ColsumPack g{};
+  int ctas = 0, c = 0;
+  for (int i = 0; i < count; ++i) {
+    B2G_CHECK_ARG(h_x[i] && h_out[i] && h_m[i] >= 0 && h_n[i] > 0, "small_colsum_group: bad entry %d", i);
+    g.x[c] = h_x[i]; g.out[c] = h_out[i]; g.m[c] = h_m[i]; g.n[c] = h_n[i];
+    g.cta_begin[c] = ctas;
+    ctas += (int)ceil_div(h_n[i], 32);
+    ++c;
+  }
+  g.cta_begin[c] = ctas;
+  g.count = c;
+  if (ctas == 0) return B2G_OK;
+  k_colsum_group<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream_>>>(g);
+  B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

@@ -267,6 +267,7 @@ class HeteroRGCN(nn.Module):
         # pass 1: per-relation products; multi-GPU tensors that need an exchange are collected so that each kind costs
         # ONE all-reduce per layer (partial type sums in forward, replicated->local gradients in backward)
         plans, partial_aggs, local_ys = {}, [], []
+        pending_y = []      # (ys list, position, x_src, W_l): the few-source products of ALL destinations, issued as one group
         for dst, ets in by_dst.items():
             # multi-GPU: rows of the sharded type are rank-local work; every other destination type is replicated work
             rep = dctx if (dctx is not None and dst != sharded) else None
@@ -282,10 +283,10 @@ class HeteroRGCN(nn.Module):
                 partial_sources = rep is not None and not src_replicated    # this rank holds only some of the sources
                 if rel.n_src < rel.n_dst and not partial_sources:   # few sources: transform them first, then aggregate
                     small_rels.append(rel)
-                    y = ops.linear(x[et[0]], rep_param(w_l, dctx if src_replicated else None), None)
+                    pending_y.append((ys, len(ys), x[et[0]], rep_param(w_l, dctx if src_replicated else None)))
                     if src_replicated and rep is None:     # replicated table consumed by this rank's rows only
                         local_ys.append((ys, len(ys)))
-                    ys.append(y)
+                    ys.append(None)
                 else:                              # many sources: aggregate first, then transform
                     agg = ops.MeanAggFn.apply(x[et[0]], rel)
                     if partial_sources:            # partial mean over this rank's sources -> sum over ranks
@@ -293,16 +294,29 @@ class HeteroRGCN(nn.Module):
                     aggs.append(agg)
                     wls.append(rep_param(w_l, rep))
             plans[dst] = (w_root, b_root, small_rels, ys, aggs, wls)
+        if pending_y:
+            for (lst, i, _, _), y in zip(pending_y, ops.linear_group([p[2] for p in pending_y], [p[3] for p in pending_y])):
+                lst[i] = y
         if dctx is not None:
             for (lst, i), t in zip(partial_aggs, partial_to_replicated_many([lst[i] for lst, i in partial_aggs], dctx)):
                 lst[i] = t
             for (lst, i), t in zip(local_ys, replicated_to_local_many([lst[i] for lst, i in local_ys], dctx)):
                 lst[i] = t
-        # pass 2: one fused SageDstFn per destination type
+        # pass 2: one fused SageDstFn per destination type; the few-row destinations with a single aggregated relation
+        # (labs, diagnoses, medications) share ONE grouped launch each way
         out = {}
+        grouped = [dst for dst, (w_root, b_root, small_rels, ys, aggs, wls) in plans.items()
+                   if not small_rels and len(aggs) == 1 and x[dst].shape[0] <= ops.SMALL_ROWS and b_root is not None]
+        if len(grouped) >= 2:
+            n = len(grouped)
+            res = ops.SageTypeDstGroupFn.apply(n, *[x[d] for d in grouped], *[plans[d][0] for d in grouped], *[plans[d][1] for d in grouped],
+                                               *[plans[d][4][0] for d in grouped], *[plans[d][5][0] for d in grouped])
+            for d, o in zip(grouped, res):
+                out[d] = o
         for dst, (w_root, b_root, small_rels, ys, aggs, wls) in plans.items():
-            out[dst] = ops.SageDstFn.apply(x[dst], w_root, b_root, tuple(small_rels), len(aggs), *ys, *aggs, *wls)
-        return out
+            if dst not in out:
+                out[dst] = ops.SageDstFn.apply(x[dst], w_root, b_root, tuple(small_rels), len(aggs), *ys, *aggs, *wls)
+        return {dst: out[dst] for dst in plans}
 
     def _gnn(self, x: Dict[str, torch.Tensor], gi: GraphIndex, streams: _DropoutStreams) -> Dict[str, torch.Tensor]:
         training = self.training

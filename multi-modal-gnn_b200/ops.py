@@ -149,6 +149,49 @@ def linear_bwd_weight_(dy, x, dw, db):
                                          ws.numel(), _stream())
 
 
+# ---- grouped small GEMMs (type-node rows) -----------------------------------------------------------------------------------
+GROUP_MAX = 12
+SMALL_ROWS = 1024
+
+
+def small_gemm_group_(problems):
+    """problems: list of dicts with keys c, a, b (tensors), optional a2, b2, bias, and flags a_t, b_nk, acc; m/n/k are
+    taken from c and the operands.  One launch per <= 12 problems."""
+    lib = _lib.load()
+    for s0 in range(0, len(problems), GROUP_MAX):
+        grp = problems[s0:s0 + GROUP_MAX]
+        arr = (_lib.GemmProblemT * len(grp))()
+        nbytes = flops = 0
+        for i, p in enumerate(grp):
+            c, a, b = p["c"], p["a"], p["b"]
+            m, n = c.shape
+            a_t, b_nk = bool(p.get("a_t", False)), bool(p.get("b_nk", False))
+            k = a.shape[0] if a_t else a.shape[1]
+            a2, b2 = p.get("a2"), p.get("b2")
+            k2 = 0 if a2 is None else (a2.shape[0] if a_t else a2.shape[1])
+            arr[i].a, arr[i].b, arr[i].c = a.data_ptr(), b.data_ptr(), c.data_ptr()
+            arr[i].a2, arr[i].b2 = _ptr(a2), _ptr(b2)
+            arr[i].bias = _ptr(p.get("bias"))
+            arr[i].m, arr[i].n, arr[i].k, arr[i].k2 = m, n, k, k2
+            arr[i].a_transposed, arr[i].b_is_nk, arr[i].accumulate = int(a_t), int(b_nk), int(bool(p.get("acc", False)))
+            nbytes += 4 * (m * n + (m + n) * (k + k2))
+            flops += 2 * m * n * (k + k2)
+        cost(nbytes, flops)
+        _run("b2g_small_gemm_group", lib.b2g_small_gemm_group, arr, len(grp), _stream())
+
+
+def small_colsum_group_(xs, outs):
+    lib = _lib.load()
+    for s0 in range(0, len(xs), GROUP_MAX):
+        gx, go = xs[s0:s0 + GROUP_MAX], outs[s0:s0 + GROUP_MAX]
+        n = len(gx)
+        px = (ctypes.c_void_p * n)(*[t.data_ptr() for t in gx])
+        po = (ctypes.c_void_p * n)(*[t.data_ptr() for t in go])
+        pm = (ctypes.c_int * n)(*[t.shape[0] for t in gx])
+        pn = (ctypes.c_int * n)(*[t.shape[1] for t in gx])
+        _run("b2g_small_colsum_group", lib.b2g_small_colsum_group, px, po, pm, pn, n, _stream())
+
+
 def gather_reduce_(csrs: Sequence[CSR], xs: Sequence[torch.Tensor], row_scales, col_scales, out: torch.Tensor,
                    accumulate: bool):
     """out[r] (+)= sum_k row_scale_k[r] * sum_{j in row r} col_scale_k[col_j] * x_k[col_j].  Short-row CSRs are
@@ -270,6 +313,128 @@ class LinearFn(Function):
 
 def linear(x, w, b=None):
     return LinearFn.apply(x, w, b)
+
+
+class GroupedLinearFn(Function):
+    """[x_i W_i^T + b_i for i in range(n)] for n independent small problems (type-node rows) in one launch each way
+    (forward; input gradients; weight gradients; bias column sums).  Same results as n LinearFn calls."""
+
+    @staticmethod
+    def forward(ctx, n, *tensors):
+        xs = [_f32(t, "x") for t in tensors[:n]]
+        ws = [_f32(t, "weight") for t in tensors[n:2 * n]]
+        bs = [None if t is None else _f32(t, "bias") for t in tensors[2 * n:3 * n]]
+        ys = [torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device) for x, w in zip(xs, ws)]
+        small_gemm_group_([dict(c=y, a=x, b=w, b_nk=True, bias=b) for y, x, w, b in zip(ys, xs, ws, bs)])
+        ctx.save_for_backward(*xs, *ws)
+        ctx.n, ctx.has_bias = n, [b is not None for b in bs]
+        ctx.set_materialize_grads(False)       # an unused output must stay "no gradient" (SURVEY.md note N8), not zeros
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        xs, ws = saved[:n], saved[n:2 * n]
+        nig = ctx.needs_input_grad
+        dxs, dws, dbs = [None] * n, [None] * n, [None] * n
+        dgrad, wgrad, cs_x, cs_o = [], [], [], []
+        for i in range(n):
+            if dys[i] is None:
+                continue
+            dy = _f32(dys[i], "grad")
+            if nig[1 + i]:
+                dxs[i] = torch.empty_like(xs[i])
+                dgrad.append(dict(c=dxs[i], a=dy, b=ws[i]))                       # dx = dy W
+            if nig[1 + n + i]:
+                dws[i] = torch.empty_like(ws[i])
+                wgrad.append(dict(c=dws[i], a=dy, b=xs[i], a_t=True))             # dW = dy^T x
+            if ctx.has_bias[i] and nig[1 + 2 * n + i]:
+                ready = _tagged_colsum(dy)
+                if ready is not None and ready.numel() == ws[i].shape[0]:
+                    dbs[i] = ready
+                else:
+                    dbs[i] = torch.empty(ws[i].shape[0], dtype=torch.float32, device=dy.device)
+                    cs_x.append(dy)
+                    cs_o.append(dbs[i])
+        if dgrad:
+            small_gemm_group_(dgrad)
+        if wgrad:
+            small_gemm_group_(wgrad)
+        if cs_x:
+            small_colsum_group_(cs_x, cs_o)
+        return (None, *dxs, *dws, *dbs)
+
+
+def linear_group(xs, ws, bs=None):
+    """n small linears at once; falls back to one call each when a problem is not small."""
+    n = len(xs)
+    bs = list(bs) if bs is not None else [None] * n
+    if n == 0:
+        return []
+    if n == 1 or any(x.shape[0] > SMALL_ROWS for x in xs):
+        return [linear(x, w, b) for x, w, b in zip(xs, ws, bs)]
+    return list(GroupedLinearFn.apply(n, *xs, *ws, *bs))
+
+
+class SageTypeDstGroupFn(Function):
+    """SageDstFn for several destination node types with few rows (labs, diagnoses, medications), each with one aggregated
+    relation:  out_t = x_t W_root,t^T + b_root,t + agg_t W_l,t^T  -- all destinations in ONE launch (the two products of a
+    destination share its output tile), and three launches backward (input gradients, weight gradients, bias sums)."""
+
+    @staticmethod
+    def forward(ctx, n, *tensors):
+        xs = [_f32(t, "x_dst") for t in tensors[:n]]
+        wr = [_f32(t, "W_root") for t in tensors[n:2 * n]]
+        br = [None if t is None else _f32(t, "b_root") for t in tensors[2 * n:3 * n]]
+        ag = [_f32(t, "agg") for t in tensors[3 * n:4 * n]]
+        wl = [_f32(t, "W_l") for t in tensors[4 * n:5 * n]]
+        outs = [torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device) for x, w in zip(xs, wr)]
+        small_gemm_group_([dict(c=o, a=x, b=w, b_nk=True, a2=a, b2=l, bias=b) for o, x, w, b, a, l in zip(outs, xs, wr, br, ag, wl)])
+        ctx.save_for_backward(*xs, *wr, *ag, *wl)
+        ctx.n, ctx.has_bias = n, [b is not None for b in br]
+        ctx.set_materialize_grads(False)       # an unused destination (note N8) must yield None gradients, not zeros
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        n = ctx.n
+        sv = ctx.saved_tensors
+        xs, wr, ag, wl = sv[:n], sv[n:2 * n], sv[2 * n:3 * n], sv[3 * n:4 * n]
+        nig = ctx.needs_input_grad
+        dxs, dwr, dbr, dag, dwl = ([None] * n for _ in range(5))
+        dgrad, wgrad, cs_x, cs_o = [], [], [], []
+        for i in range(n):
+            if douts[i] is None:          # this destination's output is unused (SURVEY.md note N8): no gradient at all
+                continue
+            do = _f32(douts[i], "grad")
+            if nig[1 + i]:
+                dxs[i] = torch.empty_like(xs[i])
+                dgrad.append(dict(c=dxs[i], a=do, b=wr[i]))
+            if nig[1 + 3 * n + i]:
+                dag[i] = torch.empty_like(ag[i])
+                dgrad.append(dict(c=dag[i], a=do, b=wl[i]))
+            if nig[1 + n + i]:
+                dwr[i] = torch.empty_like(wr[i])
+                wgrad.append(dict(c=dwr[i], a=do, b=xs[i], a_t=True))
+            if nig[1 + 4 * n + i]:
+                dwl[i] = torch.empty_like(wl[i])
+                wgrad.append(dict(c=dwl[i], a=do, b=ag[i], a_t=True))
+            if ctx.has_bias[i] and nig[1 + 2 * n + i]:
+                ready = _tagged_colsum(do)
+                if ready is not None and ready.numel() == wr[i].shape[0]:
+                    dbr[i] = ready
+                else:
+                    dbr[i] = torch.empty(wr[i].shape[0], dtype=torch.float32, device=do.device)
+                    cs_x.append(do)
+                    cs_o.append(dbr[i])
+        if dgrad:
+            small_gemm_group_(dgrad)
+        if wgrad:
+            small_gemm_group_(wgrad)
+        if cs_x:
+            small_colsum_group_(cs_x, cs_o)
+        return (None, *dxs, *dwr, *dbr, *dag, *dwl)
 
 
 class BNActDropFn(Function):
