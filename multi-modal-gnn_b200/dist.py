@@ -159,6 +159,7 @@ class PartialToReplicatedManyFn(Function):
         for x in xs:
             outs.append(flat[off:off + x.numel()].view_as(x))
             off += x.numel()
+        ctx.set_materialize_grads(False)     # an unused aggregate keeps "no gradient" (None), see ScaleGradFn
         return tuple(outs)
 
     @staticmethod
@@ -198,11 +199,12 @@ class ScaleGradFn(Function):
     @staticmethod
     def forward(ctx, x, s: float):
         ctx.s = s
+        ctx.set_materialize_grads(False)     # "no gradient" must stay None (SURVEY.md note N8), never become zeros
         return x.view_as(x)
 
     @staticmethod
     def backward(ctx, g):
-        return g * ctx.s, None
+        return (None if g is None else g * ctx.s), None
 
 
 def replicated_to_local(x, dctx: Optional[DistContext]):

@@ -293,11 +293,14 @@ class LinearFn(Function):
         linear_fwd_(x, w, b, y)
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
+        ctx.set_materialize_grads(False)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
+        if dy is None:
+            return None, None, None
         dy = _f32(dy, "grad")
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
@@ -654,6 +657,7 @@ class MeanAggFn(Function):
         x_src = _f32(x_src, "x_src")
         dn = _dense_of(rel, x_src.shape[1])
         ctx.rel, ctx.dn = rel, dn
+        ctx.set_materialize_grads(False)                  # an aggregate nobody differentiates (note N8) costs no backward work
         if dn is not None and not dn.big_is_dst:          # many sources -> few destinations: diag(1/deg_dst) D^T x_src
             return _row_scale(_adjT_times_rows(dn, x_src), rel.by_dst.inv_deg)
         out = torch.empty((rel.n_dst, x_src.shape[1]), dtype=torch.float32, device=x_src.device)
@@ -665,6 +669,8 @@ class MeanAggFn(Function):
     @staticmethod
     def backward(ctx, dout):
         rel, dn = ctx.rel, ctx.dn
+        if dout is None:
+            return None, None
         dout = _f32(dout, "grad")
         if dn is not None and not dn.big_is_dst:          # dx_src = D (dout / deg_dst)
             dx = torch.empty((rel.n_src, dout.shape[1]), dtype=torch.float32, device=dout.device)
