@@ -83,3 +83,33 @@ def test_model_state_dict_layout(pkg, golden_c1):
     assert model.embeddings["lab"].weight.shape == (50, 128)
     with pytest.raises(NotImplementedError):
         M.build_model({"model": dict(cfg["model"], architecture="HGT")}, (pkg.synth.NODE_TYPES, pkg.synth.EDGE_TYPES), None)
+
+
+def test_new_entry_points_have_no_cpu_path(pkg):
+    """optim.FusedAdam, metrics.evaluate_predictions and model.impute_missing run only on the CUDA kernels: CPU tensors
+    must raise (there is no fallback to torch / numpy), and the peer communicator is never built without a CUDA device."""
+    L = importlib.import_module(PKG + "._lib")
+    O = importlib.import_module(PKG + ".optim")
+    MX = importlib.import_module(PKG + ".metrics")
+    D = importlib.import_module(PKG + ".dist")
+    p = torch.zeros(8, requires_grad=True)
+    opt = O.FusedAdam([p], lr=1e-3, weight_decay=1e-5)
+    assert set(torch.optim.Adam([torch.zeros(1)]).defaults) <= set(opt.defaults)      # state_dict layout of torch.optim.Adam
+    opt.step()                                   # no gradient anywhere: nothing to do, nothing raised (note N8)
+    assert len(opt.state[p]) == 0
+    p.grad = torch.ones(8)
+    with pytest.raises(L.B2GError):
+        opt.step()
+    with pytest.raises(L.B2GError):
+        MX.evaluate_predictions(torch.zeros(4), torch.zeros(4), torch.zeros(4, dtype=torch.int64), 2)
+    # _metrics_from_sums == evaluate.py:36-82 on sufficient statistics (sklearn's corner cases included)
+    m = MX._metrics_from_sums(4, 2.0, 2.0, 10.0, 30.0, 0.5, 4)           # targets 1,2,3,4: SS_tot = 30 - 100/4 = 5
+    assert abs(m["mae"] - 0.5) < 1e-12 and abs(m["rmse"] - 0.5 ** 0.5) < 1e-12 and abs(m["r2"] - 0.6) < 1e-12
+    assert abs(m["mape"] - 12.5) < 1e-12
+    assert MX._metrics_from_sums(3, 0.0, 0.0, 6.0, 12.0, 0.0, 3)["r2"] == 1.0      # constant targets, perfect predictions
+    assert MX._metrics_from_sums(3, 1.0, 1.0, 6.0, 12.0, 0.0, 3)["r2"] == 0.0      # constant targets, imperfect
+    import math
+    assert math.isnan(MX._metrics_from_sums(0, 0, 0, 0, 0, 0, 0)["mae"])
+    # flat gradient buffer: padded to the peer all-reduce's 16-byte unit
+    flat = D._flat_padded([torch.ones(3), torch.ones(6)])
+    assert flat.numel() == 12 and float(flat.sum()) == 9.0
