@@ -364,7 +364,7 @@ def run_ours(args):
             per_step = dctx.n_collectives_per_step or 0
             parallelism = (f"patient-partitioned x{world}, exact mode: {per_step} exchanges per step (incl. the gradient all-reduce), "
                            + (f"{dctx.n_peer_per_step} of them one-shot NVLink peer-memory kernels of libb2g (BatchNorm ones fused into the "
-                              f"reduction kernel), rest NCCL" if dctx.peer is not None else "all NCCL") + ", captured in the step's CUDA graph")
+                              f"reduction kernel), rest NCCL" if dctx.peer is not None else "all NCCL" + (f" (peer-memory communicator unavailable: {dctx.peer_unavailable})" if dctx.peer_unavailable else "")) + ", captured in the step's CUDA graph")
         edges_per_step = NUM_LAYERS * spec.directed_edges_per_layer * world
         line = {"metric": METRIC, "value": edges_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -86,6 +86,9 @@ extern "C" int b2g_comm_create(int rank, int world, void* local_region, const un
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) {
       b2g::set_error("comm_create: cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
+      (void)cudaGetLastError();                       // do not leave the error for the next launch check to trip over
+      for (int q = 0; q < r; ++q)
+        if (c->opened[q]) cudaIpcCloseMemHandle(c->opened[q]);
       delete c;
       return B2G_ECUDA;
     }

@@ -44,15 +44,27 @@ class PeerComm:
             raise _lib.B2GError("PeerComm supports at most 8 ranks (one NVSwitch node)")
         region = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
+
+        def agree(ok: bool, what: str):
+            """Every rank learns whether the step succeeded everywhere (a rank that raised alone would leave the others
+            hanging in the next collective)."""
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                msg = lib.b2g_last_error()
+                raise _lib.B2GError(f"peer-memory communicator: {what} failed on at least one rank"
+                                    + (f" (this rank: {msg.decode()})" if (not ok and msg) else ""))
+
         with torch.cuda.device(device):
-            _lib.check(lib.b2g_comm_local_alloc(ctypes.byref(region), handle), "b2g_comm_local_alloc")
+            rc = lib.b2g_comm_local_alloc(ctypes.byref(region), handle)
+            agree(rc == 0, "cudaMalloc / cudaIpcGetMemHandle of the symmetric region")
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(handle.raw), group=group)    # also the "everybody allocated" rendezvous
             comm = ctypes.c_void_p()
-            _lib.check(lib.b2g_comm_create(self.rank, self.world, region, b"".join(handles), ctypes.byref(comm)), "b2g_comm_create")
+            rc = lib.b2g_comm_create(self.rank, self.world, region, b"".join(handles), ctypes.byref(comm))
+            agree(rc == 0, "cudaIpcOpenMemHandle of a peer's region")          # also: every rank has mapped every region
         self.handle = comm
         self.max_bytes = int(lib.b2g_comm_max_bytes())
-        dist.barrier(group=group)          # every rank has mapped every region before the first kernel signals
 
     def usable(self, t: torch.Tensor) -> bool:
         nbytes = t.numel() * t.element_size()
@@ -90,8 +102,15 @@ class DistContext:
         if peer is None:
             peer = os.environ.get("B2G_PEER_COMM", "1") != "0"
         self.peer: Optional[PeerComm] = None
+        self.peer_unavailable: Optional[str] = None
         if peer and device is not None and torch.device(device).type == "cuda" and self.world > 1:
-            self.peer = PeerComm(self.group, torch.device(device))
+            try:
+                self.peer = PeerComm(self.group, torch.device(device))
+            except Exception as exc:      # e.g. CUDA IPC not permitted in this container, GPUs without peer access: every
+                import sys                # rank lands here together (PeerComm agrees on failures), the exchanges stay on NCCL
+                self.peer_unavailable = str(exc)
+                print(f"[multi-modal-gnn_b200] peer-memory communicator unavailable, using NCCL for the step's exchanges: {exc}",
+                      file=sys.stderr, flush=True)
 
     def all_reduce_(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
         if self.trace is not None:
