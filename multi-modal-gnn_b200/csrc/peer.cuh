@@ -14,7 +14,9 @@
 // Sequence numbers live in device memory and are advanced by the kernel itself, so a captured CUDA graph can be
 // replayed.  Two parities make the scheme safe without a second barrier: nobody can reach call n+2 on a slot (and
 // overwrite the parity of call n) before everybody has signalled call n+1, i.e. finished reading call n.
-// A spin that does not complete within ~1 s sets the error flag and gives up instead of hanging the GPU.
+// A spin that does not complete within ~30 s (ranks can be skewed by seconds while they build their graph indices or load
+// modules) sets the error flag and gives up instead of hanging the GPU; once the flag is set every later wait returns at
+// once, so a dead peer costs one timeout, not one per exchange.
 #pragma once
 #include "common.cuh"
 
@@ -80,12 +82,13 @@ __device__ __forceinline__ void peer_signal_wait(const PeerCtx& c, int slot, uin
     st_volatile_u32(reinterpret_cast<uint32_t*>(c.base[r]) + (size_t)slot * PEER_MAX_WORLD + c.rank, seq);
     const uint32_t* f = reinterpret_cast<const uint32_t*>(c.base[c.rank]) + (size_t)slot * PEER_MAX_WORLD + r;
     bool ok = false;
-    for (int it = 0; it < (1 << 22); ++it) {
+    const bool dead = *reinterpret_cast<volatile int*>(c.error) != 0;      // an earlier wait already timed out
+    for (int it = 0; it < (dead ? 1 : (1 << 25)); ++it) {
       if ((int32_t)(ld_volatile_u32(f) - seq) >= 0) {
         ok = true;
         break;
       }
-      if (it > 4096) __nanosleep(200);
+      if (it > 4096) __nanosleep(it > (1 << 16) ? 1000 : 200);             // ~30 s in total
     }
     if (!ok) *c.error = 1;
     __threadfence_system();
