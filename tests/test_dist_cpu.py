@@ -267,6 +267,8 @@ def _partitioned_step(rank, world, spec_seed):
     return worst
 
 
-def test_partitioned_step_equals_single_process_gloo():
-    out = _spawn(_partitioned_step, 2, 4)
-    assert max(out.values()) <= 2e-3
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_step_equals_single_process_gloo(world):
+    """world 3: an odd split, so the partitions are of unequal size and the middle rank has two neighbours."""
+    out = _spawn(_partitioned_step, world, 4)
+    assert len(out) == world and max(out.values()) <= 2e-3
