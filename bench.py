@@ -192,6 +192,52 @@ class ClockSampler:
         return out
 
 
+def layer_microbench(model, trainer, spec, dev, flush, peak_gbs, reps=5):
+    """ONE HeteroConv layer (all six relations incl. their SAGE linears, no BatchNorm / decoder),
+    forward + backward, against the layer's compulsory HBM traffic bytes_min = 5 N_p d 4 + 2 E 4 + 6 (N_p + 1) 4 (read x_p,
+    write out_p, CSR once; backward: read grad_out_p and x_p, write grad_x_p, CSR again).  Each repetition is enqueued behind
+    a spin kernel, so the event pair brackets back-to-back device work.  Single GPU only."""
+    import torch
+    gi = model._graph_index(trainer.data)
+    d = model.hidden_dim
+    gen = torch.Generator(device=dev).manual_seed(7)
+    counts = {nt: int(trainer.data[nt].num_nodes) for nt in trainer.data.node_types}
+    x = {nt: torch.randn(n, d, device=dev, generator=gen).requires_grad_(True) for nt, n in counts.items()}
+    gout = {nt: torch.randn(n, d, device=dev, generator=gen) for nt, n in counts.items()}
+    params = [p for p in model.convs[0].parameters()]
+
+    def once():
+        for t in list(x.values()) + params:
+            t.grad = None
+        out = model._layer(0, x, gi)
+        torch.autograd.backward([out[nt] for nt in out], [gout[nt] for nt in out])
+
+    was_training = model.training
+    model.train()
+    for _ in range(2):
+        once()
+    torch.cuda.synchronize()
+    times = []
+    for i in range(reps):
+        flush.fill_(i & 0xFF)
+        torch.cuda._sleep(int(0.010 * 1.9e9))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        once()
+        e.record()
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e))
+    for t in params:
+        t.grad = None
+    model.train(was_training)
+    ms = statistics.median(times)
+    e_und = spec.e_lab + spec.e_dx + spec.e_med
+    bytes_min = 5 * spec.n_patient * d * 4 + 2 * e_und * 4 + 6 * (spec.n_patient + 1) * 4
+    return {"what": "one HeteroConv layer (6 relations + SAGE linears) forward + backward, eager behind a spin kernel, median of %d" % reps,
+            "ms": ms, "directed_edges_per_s": spec.directed_edges_per_layer / (ms * 1e-3), "bytes_min": bytes_min,
+            "achieved_GBps_of_bytes_min": bytes_min / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": bytes_min / (ms * 1e-3) / 1e9 / peak_gbs}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -380,6 +426,11 @@ def run_ours(args):
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels, "final_loss": final_loss,
                 "step_ms_min_max": [min(step_ms), max(step_ms)]}
+        if world == 1:
+            try:        # an extra, never a reason to lose the line
+                line["layer_microbench"] = layer_microbench(model, trainer, spec, dev, flush, _peaks()["hbm"])
+            except Exception as exc:      # noqa: BLE001
+                line["layer_microbench"] = {"error": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:
             v, ms, sample, cores = cpu_baseline_run(args.workload, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
