@@ -113,3 +113,29 @@ def test_new_entry_points_have_no_cpu_path(pkg):
     # flat gradient buffer: padded to the peer all-reduce's 16-byte unit
     flat = D._flat_padded([torch.ones(3), torch.ones(6)])
     assert flat.numel() == 12 and float(flat.sum()) == 9.0
+
+
+def test_c4_shard_spec_is_one_eighth_of_c4(pkg):
+    c4, sh = pkg.synth.SPECS["C4"], pkg.synth.SPECS["C4s8"]
+    assert sh.n_patient * 8 == c4.n_patient and sh.e_lab * 8 == c4.e_lab and sh.e_dx * 8 == c4.e_dx and sh.e_med * 8 == c4.e_med
+    assert (sh.n_lab, sh.n_dx, sh.n_med, sh.low_degree_frac) == (c4.n_lab, c4.n_dx, c4.n_med, c4.low_degree_frac)
+    assert sh.directed_edges_per_layer * 8 == c4.directed_edges_per_layer
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` is CPU-only (the oracle port on a bounded sample): run it here and check the JSON contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train_edges_per_sec_fwd_bwd_per_heteroconv_step" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "C2" and "sample" in d["config"]
