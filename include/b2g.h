@@ -114,6 +114,52 @@ int b2g_dense_adjacency(const int32_t* rowptr, const int32_t* col, const float* 
 int b2g_transpose_pad(const float* in, const float* scale, int rows, int cols, int pad, float* out, void* stream);
 int b2g_row_scale(const float* in, const float* scale, int64_t rows, int d, float* out, void* stream);
 
+/* (b') The patient side of a whole HeteroConv layer in one launch per direction (csrc/layer_tc.cu) -- replaces, for the
+ * three type -> patient relations and the three patient -> type relations of model.py:125-131,256 together, PyG's
+ * SAGEConv.propagate + lin_l + lin_r + HeteroConv's stack().sum(0) on the patient rows.
+ * The patient x type adjacency of all relations is ONE bit matrix bits[N_patient, nw] (32 type columns per word; relation r
+ * owns the column range [bit_off_r, bit_off_r + n_type_r)); b2g_bit_layout_t says, per word, which relation its low bits
+ * [0, split) and high bits [split, 32) belong to (split = 32: one relation; at most one boundary per word), so that a per
+ * relation row scale (1/deg of the patient, PyG's mean) can be applied while the bits are expanded into TF32 tiles. */
+typedef struct {
+  int32_t nw;           /* words per row, <= 24 */
+  int8_t rel_a[24];     /* relation (index into h_rscale) of bits [0, split) of word k   */
+  int8_t rel_b[24];     /* relation of bits [split, 32)                                   */
+  int8_t split[24];     /* 1..32                                                          */
+} b2g_bit_layout_t;
+/* bits[row, (bit_off + col[j]) / 32] |= 1 << ((bit_off + col[j]) % 32) for every neighbour j of `row` in a by-patient CSR.
+ * `bits` must be zeroed by the caller before the first relation is added. */
+int b2g_adj_bits_build(const int32_t* rowptr, const int32_t* col, int64_t n_rows, int nw, int bit_off, uint32_t* bits,
+                       void* stream);
+/* out[n, ktot] = [ W (or W^T) | tab_0^T * scale_0 | tab_1^T * scale_1 | ... ] : the reduction operand of b2g_layer_fwd_tc.
+ * W = sum of the n_w (<= 4) matrices h_ws[i] (HeteroConv sums the lin_r products of all relations that share a destination),
+ * each [n, kx] (w_transposed = 0: nn.Linear weight, y = x W^T) or [kx, n] (w_transposed = 1: dx = dy W); tab_r is
+ * [rows_r, n] and lands in columns kx + off_r .. ; scale_r [rows_r] or NULL; all other columns are zero.
+ * bias_out[n] = sum of the n_b biases (n_b = 0: untouched).  h_* are HOST arrays of device pointers / ints. */
+int b2g_layer_cat_weights(const float* const* h_ws, int n_w, int w_transposed, const float* const* h_biases, int n_b,
+                          float* bias_out, int n, int kx, const float* const* h_tabs, const float* const* h_scales,
+                          const int* h_rows, const int* h_offs, int n_rel, int ktot, float* out, void* stream);
+/* y[m, n] = x[m, kx] . wcat[:, :kx]^T + (diag(rscale) A)[m, 32 nw] . wcat[:, kx:]^T + bias      (tcgen05, TF32 operands)
+ *   forward : x = x_patient, wcat = [sum_r W_r,root | Y_lab | Y_dx | Y_med] with Y_r = x_r W_l,r^T, rscale_r = 1/deg_r(patient)
+ *   backward: x = dout_patient, wcat = [W_root^T | dagg_r / deg_r(type)], rscale = NULL  ->  dx_patient
+ * K-chunk pipelined: TMA (x chunk, wcat chunk) + expander warps (bits -> swizzled TF32 A chunk) -> tcgen05.mma -> TMEM,
+ * double-buffered accumulator, epilogue TMEM -> staging -> coalesced stores.  stat_sums (optional, n <= 128): fp64
+ * {sum, sum of squares} per column of y (BatchNorm statistics of the layer output, model.py:259-261) produced by the
+ * epilogue; ws: b2g_layer_stats_ws_bytes(n) (only when stat_sums is given). */
+int b2g_layer_fwd_tc_supported(int64_t m, int n, int kx, int nw);
+size_t b2g_layer_stats_ws_bytes(int n);
+int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* bias, const uint32_t* bits,
+                     const b2g_bit_layout_t* h_layout, const float* const* h_rscale, int64_t m, int n, int kx, float* y,
+                     double* stat_sums, void* ws, size_t ws_bytes, void* stream);
+/* out[32 nw, 128] = col_scale[:, None] * (diag(rscale) A)^T . x[m, 128]       (tcgen05, MN-major TF32 operands)
+ *   forward : x = x_patient, col_scale = 1/deg(type)  -> mean of the patient neighbours of every type node
+ *   backward: x = dout_patient, rscale_r = 1/deg_r(patient) -> dY_r
+ * ws: b2g_layer_adjT_tc_ws_bytes(nw).  Supported for d = 128 and nw <= 16. */
+int b2g_layer_adjT_tc_supported(int64_t m, int d, int nw);
+size_t b2g_layer_adjT_tc_ws_bytes(int nw);
+int b2g_layer_adjT_tc(const float* x, const uint32_t* bits, const b2g_bit_layout_t* h_layout, const float* const* h_rscale,
+                      const float* col_scale, int64_t m, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (c) embedding tables -- nn.Embedding(arange(N)) fwd / dense grad (model.py:225-226)
  * ---------------------------------------------------------------------------------------------- */

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb2g.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["graph.cu", "spmm.cu", "dense.cu", "norm.cu", "decoder.cu", "dense_tc.cu"]
+SOURCES = ["graph.cu", "spmm.cu", "dense.cu", "norm.cu", "decoder.cu", "dense_tc.cu", "layer_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -35,6 +35,11 @@ class GemmProblemT(ctypes.Structure):
                 ("m", ctypes.c_int32), ("n", ctypes.c_int32), ("k", ctypes.c_int32), ("k2", ctypes.c_int32),
                 ("a_transposed", ctypes.c_int32), ("b_is_nk", ctypes.c_int32), ("accumulate", ctypes.c_int32),
                 ("reserved", ctypes.c_int32)]
+
+
+class BitLayoutT(ctypes.Structure):
+    """b2g_bit_layout_t"""
+    _fields_ = [("nw", ctypes.c_int32), ("rel_a", ctypes.c_int8 * 24), ("rel_b", ctypes.c_int8 * 24), ("split", ctypes.c_int8 * 24)]
 
 
 def _sources():
@@ -156,6 +161,17 @@ _PROTOS = {
                                 _P, _P, _P, c_size_t, _P]),
     "b2g_decoder_bwd_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, c_uint64, _P, _P, _P, _P,
                                    _P, _P, _P, c_size_t, _P]),
+    "b2g_adj_bits_build": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),
+    "b2g_layer_cat_weights": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, ctypes.POINTER(c_void_p), c_int, _P, c_int, c_int,
+                                      ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                      c_int, c_int, _P, _P]),
+    "b2g_layer_fwd_tc_supported": (c_int, [c_int64, c_int, c_int, c_int]),
+    "b2g_layer_stats_ws_bytes": (c_size_t, [c_int]),
+    "b2g_layer_fwd_tc": (c_int, [_P, _P, _P, _P, ctypes.POINTER(BitLayoutT), ctypes.POINTER(c_void_p), c_int64, c_int, c_int, _P, _P, _P,
+                                 c_size_t, _P]),
+    "b2g_layer_adjT_tc_supported": (c_int, [c_int64, c_int, c_int]),
+    "b2g_layer_adjT_tc_ws_bytes": (c_size_t, [c_int]),
+    "b2g_layer_adjT_tc": (c_int, [_P, _P, ctypes.POINTER(BitLayoutT), ctypes.POINTER(c_void_p), _P, c_int64, _P, _P, c_size_t, _P]),
     "b2g_loss_ws_bytes": (c_size_t, [c_int64]),
     "b2g_weighted_loss": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
 }

@@ -152,6 +152,132 @@ class DenseAdjacency:
         self.mat, self.pad, self.n_small, self.n_big, self.big_is_dst = mat, pad, n_small, n_big, big_is_dst
 
 
+def bit_layout(sizes):
+    """Column offsets of consecutive relations (sizes[i] type nodes each) on the concatenated bit axis such that no 32-bit
+    word contains more than one relation boundary, and the per-word description the kernels need.
+    Returns (offsets, nw, rel_a, rel_b, split)."""
+    offs, off, last_boundary_word = [], 0, -1
+    for n in sizes:
+        start = off
+        if start % 32 != 0:
+            w = start // 32
+            if w == last_boundary_word:            # this word already holds a boundary: start the relation at the next word
+                start = (w + 1) * 32
+            else:
+                last_boundary_word = w
+        offs.append(start)
+        off = start + int(n)
+    nw = max(1, (off + 31) // 32)
+    owner = [-1] * (32 * nw)
+    for i, (o, n) in enumerate(zip(offs, sizes)):
+        for c in range(o, o + int(n)):
+            owner[c] = i
+    rel_a, rel_b, split = [], [], []
+    for w in range(nw):
+        seen = []
+        for b in range(32):
+            r = owner[32 * w + b]
+            if r >= 0 and (not seen or seen[-1][0] != r):
+                seen.append((r, b))
+        assert len(seen) <= 2, "bit layout: more than one relation boundary in a word"
+        if not seen:
+            rel_a.append(0); rel_b.append(0); split.append(32)
+        elif len(seen) == 1:
+            rel_a.append(seen[0][0]); rel_b.append(seen[0][0]); split.append(32)
+        else:
+            rel_a.append(seen[0][0]); rel_b.append(seen[1][0]); split.append(seen[1][1])
+    return offs, nw, rel_a, rel_b, split
+
+
+class PatientBits:
+    """Bit-matrix form of every relation between the hub node type (patient) and the small vocabularies
+    (graph_build.py:216-247: every edge is patient <-> lab / diagnosis / medication) for the single-launch HeteroConv
+    kernels (csrc/layer_tc.cu).  `types[i]` owns the bit columns [offs[i], offs[i] + n_i):
+
+      bits_in   rows = patients, bit (p, t) set when edge t -> p exists in the relation (t, *, patient)   (forward out_p, dY)
+      bits_out  same for the relation (patient, *, t)                                                    (type sums, dx_p)
+
+    The reference builds every reverse relation as edge_index.flip(0) (graph_build.py:222,235,247), so the two matrices
+    are normally identical and share storage."""
+
+    MAX_TYPES = 4
+
+    def __init__(self, gi: "GraphIndex", hub: str):
+        lib = _lib.load()
+        self.hub = hub
+        n_hub = gi.node_counts[hub]
+        self.types, self.in_rel, self.out_rel = [], [], []
+        self.ok = True
+        for et, rel in gi.relations.items():
+            src, _, dst = et
+            if src == hub and dst == hub:
+                self.ok = False
+            other = dst if src == hub else (src if dst == hub else None)
+            if other is None:
+                self.ok = False          # a relation that does not touch the hub type: not this graph family
+                continue
+            if other not in self.types:
+                self.types.append(other)
+                self.in_rel.append(None)
+                self.out_rel.append(None)
+            i = self.types.index(other)
+            slot = self.out_rel if src == hub else self.in_rel
+            if slot[i] is not None:
+                self.ok = False          # two relations between the same pair of types
+            slot[i] = rel
+        if not self.types or len(self.types) > self.MAX_TYPES:
+            self.ok = False
+        if not self.ok:
+            return
+        sizes = [gi.node_counts[t] for t in self.types]
+        self.sizes = sizes
+        self.offs, self.nw, rel_a, rel_b, split = bit_layout(sizes)
+        if self.nw > 24:
+            self.ok = False
+            return
+        self.layout = _lib.BitLayoutT()
+        self.layout.nw = self.nw
+        for k in range(self.nw):
+            self.layout.rel_a[k], self.layout.rel_b[k], self.layout.split[k] = rel_a[k], rel_b[k], split[k]
+        dev = next(iter(gi.relations.values())).by_dst.rowptr.device
+        self.device = dev
+
+        def build(rels, by):
+            if all(r is None for r in rels):
+                return None
+            bits = torch.zeros((n_hub, self.nw), dtype=torch.int32, device=dev)
+            for r, off in zip(rels, self.offs):
+                if r is None or r.n_edges == 0:
+                    continue
+                csr = getattr(r, by)
+                _lib.check(lib.b2g_adj_bits_build(csr.rowptr.data_ptr(), csr.col.data_ptr(), n_hub, self.nw, int(off), bits.data_ptr(),
+                                                  _stream()), "b2g_adj_bits_build")
+            return bits
+
+        self.bits_in = build(self.in_rel, "by_dst")         # rows keyed by the destination (patient), col = source type node
+        self.bits_out = build(self.out_rel, "by_src")       # rows keyed by the source (patient), col = destination type node
+        if self.bits_in is not None and self.bits_out is not None and bool(torch.equal(self.bits_in, self.bits_out)):
+            self.bits_out = self.bits_in
+        self._col_scale = None
+
+    def rscale_in(self):
+        """per type: 1/deg of the patient in the relation type -> patient (PyG mean), or None"""
+        return [None if r is None else r.by_dst.inv_deg for r in self.in_rel]
+
+    def col_scale_out(self):
+        """[32 nw] 1/deg of every type node in its relation patient -> type (global degrees in multi-GPU mode), 0 on padding"""
+        if self._col_scale is None:
+            cs = torch.zeros(32 * self.nw, dtype=torch.float32, device=self.device)
+            for r, off, n in zip(self.out_rel, self.offs, self.sizes):
+                if r is not None:
+                    cs[off:off + n] = r.by_dst.inv_deg
+            self._col_scale = cs
+        return self._col_scale
+
+    def inv_deg_out(self):
+        return [None if r is None else r.by_dst.inv_deg for r in self.out_rel]
+
+
 class GraphIndex:
     """All relations of one heterogeneous graph + node counts."""
 
@@ -175,6 +301,14 @@ class GraphIndex:
         lab_rel = self.relations.get(("patient", "has_lab", "lab"))
         # model.py:297-298: torch.bincount(has_lab.edge_index[0], minlength=N_patient) == row degrees of the by-source CSR
         self.patient_lab_degree: Optional[torch.Tensor] = lab_rel.by_src.deg if lab_rel is not None else None
+        self._hub_bits: Dict[str, PatientBits] = {}
+
+    def hub_bits(self, hub: str = "patient") -> Optional["PatientBits"]:
+        """Bit-matrix adjacency around `hub` for the fused layer kernels (None when the graph is not hub-shaped)."""
+        if hub not in self._hub_bits:
+            self._hub_bits[hub] = PatientBits(self, hub) if hub in self.node_counts else None
+        pb = self._hub_bits[hub]
+        return pb if (pb is not None and pb.ok) else None
 
     def matches(self, data) -> bool:
         eid = data.edge_index_dict

@@ -262,6 +262,9 @@ class HeteroRGCN(nn.Module):
         for et in self._edge_types:
             if et in gi.relations and et[0] in x and et[2] in x:
                 by_dst.setdefault(et[2], []).append(et)
+        fused = self._layer_fused(convs, x, gi, by_dst)
+        if fused is not None:
+            return fused
         dctx = self.dist
         sharded = dctx.sharded_type if dctx is not None else None
         # pass 1: per-relation products; multi-GPU tensors that need an exchange are collected so that each kind costs
@@ -317,6 +320,56 @@ class HeteroRGCN(nn.Module):
             if dst not in out:
                 out[dst] = ops.SageDstFn.apply(x[dst], w_root, b_root, tuple(small_rels), len(aggs), *ys, *aggs, *wls)
         return {dst: out[dst] for dst in plans}
+
+    def _layer_fused(self, convs, x, gi: GraphIndex, by_dst) -> Optional[Dict[str, torch.Tensor]]:
+        """The same layer with the hub (patient) side in ops.PatientSideFn: one tcgen05 launch for out_patient (self term +
+        the three type -> patient means, adjacency as bits), one for the three patient -> type neighbour sums; the few-row
+        products on the type nodes stay in the grouped small-GEMM launches.  tf32 mode, hub-shaped graphs, d = 128; returns
+        None when not applicable (the caller then runs the per-relation path)."""
+        dctx = self.dist
+        hub = dctx.sharded_type if dctx is not None else "patient"
+        if hub not in x or hub not in by_dst or ops.PRECISION != "tf32":
+            return None
+        pb = gi.hub_bits(hub)
+        if not ops.patient_side_supported(pb, x[hub].shape[0], self.hidden_dim):
+            return None
+        live = {et for ets in by_dst.values() for et in ets}
+        if live != set(gi.relations.keys()) or any(t not in x for t in pb.types):
+            return None                                   # graph relations the model does not know (or vice versa)
+        if any(x[t].shape[0] > ops.SMALL_ROWS for t in pb.types):
+            return None
+        # few-row products first: Y_t = x_t W_l^T for every relation t -> hub (replicated work in multi-GPU mode)
+        w_roots, b_roots, y_x, y_w = [], [], [], []
+        for t, rel in zip(pb.types, pb.in_rel):
+            if rel is None:
+                continue
+            conv = convs["__".join(rel.edge_type)]
+            w_roots.append(conv.lin_r.weight)
+            b_roots.append(conv.lin_l.bias)
+            y_x.append(x[t])
+            y_w.append(rep_param(conv.lin_l.weight, dctx))
+        if not w_roots:
+            return None
+        ys_live = ops.linear_group(y_x, y_w)
+        ys_live = replicated_to_local_many(ys_live, dctx)  # consumed by rank-local rows: gradients are summed over ranks
+        it = iter(ys_live)
+        ys = [None if rel is None else next(it) for rel in pb.in_rel]
+        res = ops.PatientSideFn.apply(pb, len(w_roots), x[hub], *w_roots, *b_roots, *ys)
+        out = {hub: res[0]}
+        out_types = [i for i, rel in enumerate(pb.out_rel) if rel is not None and pb.types[i] in by_dst]
+        aggs = partial_to_replicated_many([res[1 + i] for i in out_types], dctx)     # partial neighbour sums -> all ranks
+        if out_types:
+            dst_x, w_r, b_l, w_l = [], [], [], []
+            for i in out_types:
+                conv = convs["__".join(pb.out_rel[i].edge_type)]
+                dst_x.append(x[pb.types[i]])
+                w_r.append(rep_param(conv.lin_r.weight, dctx))
+                b_l.append(rep_param(conv.lin_l.bias, dctx))
+                w_l.append(rep_param(conv.lin_l.weight, dctx))
+            outs = ops.SageTypeDstGroupFn.apply(len(out_types), *dst_x, *w_r, *b_l, *aggs, *w_l)
+            for i, o in zip(out_types, outs):
+                out[pb.types[i]] = o
+        return {dst: out[dst] for dst in by_dst if dst in out}
 
     def _gnn(self, x: Dict[str, torch.Tensor], gi: GraphIndex, streams: _DropoutStreams) -> Dict[str, torch.Tensor]:
         training = self.training

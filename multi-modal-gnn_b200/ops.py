@@ -766,6 +766,153 @@ class SageDstFn(Function):
         return (dx, dw, db, None, None, *d_ys, *d_aggs, *d_wls)
 
 
+# ---- single-launch patient side of a HeteroConv layer (csrc/layer_tc.cu), tf32 mode ----------------------------------------
+def _ptr_array(ts):
+    return (ctypes.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+
+
+def layer_cat_weights_(ws_list, transposed, tabs, scales, offs, kx, ktot, n, biases=()):
+    """([sum of W (or its transpose) | tab_i^T * scale_i at column kx + offs[i]] -> [n, ktot],  sum of the biases or None)"""
+    lib = _lib.load()
+    dev = ws_list[0].device
+    out = torch.empty((n, ktot), dtype=torch.float32, device=dev)
+    biases = [b for b in biases if b is not None]
+    bias_out = torch.empty(n, dtype=torch.float32, device=dev) if biases else None
+    live = [(t, sc, o) for t, sc, o in zip(tabs, scales, offs) if t is not None]
+    nr = len(live)
+    pt = _ptr_array([t for t, _, _ in live] or [None])
+    ps = _ptr_array([sc for _, sc, _ in live] or [None])
+    rows = (ctypes.c_int * max(nr, 1))(*[int(t.shape[0]) for t, _, _ in live] or [0])
+    off = (ctypes.c_int * max(nr, 1))(*[int(o) for _, _, o in live] or [0])
+    _run("b2g_layer_cat_weights", lib.b2g_layer_cat_weights, _ptr_array(ws_list), len(ws_list), int(transposed),
+         _ptr_array(biases or [None]), len(biases), _ptr(bias_out), n, kx, pt, ps, rows, off, nr, ktot, out.data_ptr(), _stream())
+    return out, bias_out
+
+
+def layer_fwd_tc_(x, wcat, bias, bits, pb, rscales, y, stat_sums=None):
+    lib = _lib.load()
+    m, kx = x.shape
+    n = wcat.shape[0]
+    ws = None
+    if stat_sums is not None:
+        ws = workspace(lib.b2g_layer_stats_ws_bytes(n), x.device)
+    cost(4 * (m * kx + m * n) + 4 * m * pb.nw + 4 * wcat.numel(), 2 * m * n * wcat.shape[1])
+    _run("b2g_layer_fwd_tc", lib.b2g_layer_fwd_tc, x.data_ptr(), wcat.data_ptr(), _ptr(bias), bits.data_ptr(), ctypes.byref(pb.layout),
+         _ptr_array(list(rscales) + [None] * (4 - len(rscales))), m, n, kx, y.data_ptr(), _ptr(stat_sums), _ptr(ws),
+         0 if ws is None else ws.numel(), _stream())
+    return y
+
+
+def layer_adjT_tc_(x, bits, pb, rscales, col_scale):
+    """[32 nw, 128] = col_scale * (diag(rscale) A)^T x"""
+    lib = _lib.load()
+    m = x.shape[0]
+    out = torch.empty((32 * pb.nw, 128), dtype=torch.float32, device=x.device)
+    ws = workspace(lib.b2g_layer_adjT_tc_ws_bytes(pb.nw), x.device)
+    cost(4 * m * 128 + 4 * m * pb.nw + 4 * out.numel(), 2 * m * 128 * 32 * pb.nw)
+    _run("b2g_layer_adjT_tc", lib.b2g_layer_adjT_tc, x.data_ptr(), bits.data_ptr(), ctypes.byref(pb.layout),
+         _ptr_array(list(rscales) + [None] * (4 - len(rscales))), _ptr(col_scale), m, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+def patient_side_supported(pb, n_rows: int, d: int) -> bool:
+    if PRECISION != "tf32" or pb is None or d != 128 or n_rows < TC_MIN_ROWS:
+        return False
+    lib = _lib.load()
+    return bool(lib.b2g_layer_fwd_tc_supported(n_rows, d, d, pb.nw)) and bool(lib.b2g_layer_adjT_tc_supported(n_rows, d, pb.nw))
+
+
+class PatientSideFn(Function):
+    """Everything a HeteroConv layer does on the PATIENT rows (model.py:125-131,256; PyG HeteroConv(aggr='sum') of
+    SAGEConv(mean)), two launches forward and three backward, with the adjacency as a bit matrix (graph.PatientBits):
+
+        out_p   = x_p (sum_r W_root,r)^T + sum_r b_r + sum_t diag(1/deg_t(p)) A_t Y_t      Y_t = x_t W_l^T, few rows, given
+        agg_t   = diag(1/deg(t)) A_t^T x_p          for every type t with a relation patient -> t
+
+    inputs: pb, n_w, n_t, x_p, W_root_1..n_w, b_1..n_w, Y_t for t in pb.types (None: no relation t -> patient)
+    outputs: out_p, agg_t for t in pb.types (a zero-row tensor when there is no relation patient -> t)."""
+
+    @staticmethod
+    def forward(ctx, pb, n_w, x_p, *tensors):
+        nt = len(pb.types)
+        w_roots = [_f32(t, "W_root") for t in tensors[:n_w]]
+        biases = [None if t is None else _f32(t, "b_root") for t in tensors[n_w:2 * n_w]]
+        ys = [None if t is None else _f32(t, "Y") for t in tensors[2 * n_w:2 * n_w + nt]]
+        x_p = _f32(x_p, "x_patient")
+        m, d = x_p.shape
+        ktot = d + 32 * pb.nw
+        ys_in = [y if r is not None else None for y, r in zip(ys, pb.in_rel)]
+        wcat, bias = layer_cat_weights_(w_roots, False, ys_in, [None] * nt, pb.offs, d, ktot, d, biases)
+        out = torch.empty((m, d), dtype=torch.float32, device=x_p.device)
+        if pb.bits_in is not None and any(y is not None for y in ys_in):
+            layer_fwd_tc_(x_p, wcat, bias, pb.bits_in, pb, pb.rscale_in(), out)
+        else:
+            linear_fwd_(x_p, wcat[:, :d].contiguous(), bias, out)
+        aggs = []
+        if pb.bits_out is not None:
+            t_all = layer_adjT_tc_(x_p, pb.bits_out, pb, [None] * nt, pb.col_scale_out())
+            for r, off, n in zip(pb.out_rel, pb.offs, pb.sizes):
+                aggs.append(t_all[off:off + n] if r is not None else t_all[0:0])
+        else:
+            aggs = [out.new_zeros((0, d)) for _ in pb.types]
+        ctx.save_for_backward(x_p, *w_roots)
+        ctx.meta = (pb, n_w, [b is not None for b in biases], [None if y is None else tuple(y.shape) for y in ys])
+        ctx.set_materialize_grads(False)
+        return (out, *aggs)
+
+    @staticmethod
+    def backward(ctx, dout, *daggs):
+        pb, n_w, has_bias, y_shapes = ctx.meta
+        saved = ctx.saved_tensors
+        x_p, w_roots = saved[0], list(saved[1:1 + n_w])
+        nt = len(pb.types)
+        m, d = x_p.shape
+        nig = ctx.needs_input_grad            # (pb, n_w, x_p, W.., b.., Y..)
+        dev = x_p.device
+        dx = None
+        dws = [None] * n_w
+        dbs = [None] * n_w
+        dys = [None] * nt
+        live_aggs = [(None if g is None or r is None else _f32(g, "grad")) for g, r in zip(daggs, pb.out_rel)]
+        if dout is not None:
+            dout = _f32(dout, "grad")
+        if nig[2]:
+            ktot = d + 32 * pb.nw
+            if dout is None:
+                dout_x = torch.zeros_like(x_p)
+            else:
+                dout_x = dout
+            if pb.bits_out is not None and any(g is not None for g in live_aggs):
+                wcat, _ = layer_cat_weights_(w_roots, True, live_aggs, pb.inv_deg_out(), pb.offs, d, ktot, d)
+                dx = torch.empty_like(x_p)
+                layer_fwd_tc_(dout_x, wcat, None, pb.bits_out, pb, [None] * nt, dx)
+            elif dout is not None:
+                w = w_roots[0]
+                for extra in w_roots[1:]:
+                    w = w + extra
+                dx = torch.empty_like(x_p)
+                linear_bwd_input_(dout, w, dx)
+        if dout is not None:
+            need_w = any(nig[3 + i] for i in range(n_w))
+            need_b = any(has_bias[i] and nig[3 + n_w + i] for i in range(n_w))
+            if need_w or need_b:
+                dw = torch.empty((d, d), dtype=torch.float32, device=dev)
+                db = torch.empty(d, dtype=torch.float32, device=dev) if need_b else None
+                linear_bwd_weight_(dout, x_p, dw, db)
+                for i in range(n_w):
+                    if nig[3 + i]:
+                        dws[i] = dw
+                    if has_bias[i] and nig[3 + n_w + i]:
+                        dbs[i] = db
+            want_y = [y_shapes[i] is not None and pb.in_rel[i] is not None and nig[3 + 2 * n_w + i] for i in range(nt)]
+            if any(want_y) and pb.bits_in is not None:
+                dy_all = layer_adjT_tc_(dout, pb.bits_in, pb, pb.rscale_in(), None)
+                for i, (off, n) in enumerate(zip(pb.offs, pb.sizes)):
+                    if want_y[i]:
+                        dys[i] = dy_all[off:off + n]
+        return (None, None, dx, *dws, *dbs, *dys)
+
+
 class PairAddReluFn(Function):
     """z[i] = relu(U[p_i] + V[l_i]) -- the first decoder layer after factorising
     Linear(2d, 64)(cat[h_p, h_l]) = h_p W[:, :d]^T + (h_l W[:, d:]^T + b)   (model.py:305-309,324-333,373-377):

@@ -1,0 +1,212 @@
+"""GPU tests of the single-launch HeteroConv patient-side kernels (csrc/layer_tc.cu) through the C ABI.
+
+The kernels feed fp32 words to tcgen05.mma.kind::tf32, which ignores the low 13 mantissa bits of every operand.  Two
+references are used: (1) a float64 product of the operands truncated to TF32 the same way -- what the tensor core computes
+up to fp32 accumulation order, held to 2e-5 of max|ref| (catches any layout / swizzle / barrier bug); (2) the plain fp32
+product of the untruncated operands (the reference's arithmetic, model.py:125-131,256 via PyG SAGEConv mean), held to the
+north_star tolerance for tensor-core outputs (1e-2) and in practice ~1e-3."""
+import importlib
+
+import pytest
+import torch
+
+PKG = "multi-modal-gnn_b200"
+
+
+def _mods():
+    return (importlib.import_module(PKG + ".graph"), importlib.import_module(PKG + ".ops"), importlib.import_module(PKG + ".model"),
+            importlib.import_module(PKG + ".synth"), importlib.import_module(PKG + "._lib"))
+
+
+def tf32_trunc(t):
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+def relmax(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---- host logic (no GPU) ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sizes", [[50, 200, 100], [20, 30, 25], [160, 200, 100], [5, 5, 5, 40], [1], [33, 31], [256, 256, 250]])
+def test_bit_layout_one_boundary_per_word(sizes):
+    G = importlib.import_module(PKG + ".graph")
+    offs, nw, rel_a, rel_b, split = G.bit_layout(sizes)
+    assert len(offs) == len(sizes) and nw == len(rel_a) == len(rel_b) == len(split)
+    owner = {}
+    for i, (o, n) in enumerate(zip(offs, sizes)):
+        for c in range(o, o + n):
+            assert c not in owner, "relations overlap on the bit axis"
+            owner[c] = i
+    assert max(owner) < 32 * nw
+    for c, i in owner.items():          # every column resolves to its relation through (rel_a, rel_b, split)
+        w, b = divmod(c, 32)
+        assert (rel_a[w] if b < split[w] else rel_b[w]) == i
+    assert all(1 <= s <= 32 for s in split)
+
+
+# ---- kernels ---------------------------------------------------------------------------------------------------------------
+def _random_hub(G, m, sizes, density, dev, seed=0):
+    """random bipartite edges hub x type_i, as (dense 0/1 matrices, PatientBits-like object built through the library)"""
+    gen = torch.Generator().manual_seed(seed)
+    dense = [(torch.rand(m, n, generator=gen) < p).float() for n, p in zip(sizes, density)]
+    dense[0][min(3, m - 1)] = 0           # an isolated patient (mean of nothing = 0, PyG clamp(count, 1))
+    data = importlib.import_module(PKG + ".heterodata").HeteroGraph()
+    data["patient"].num_nodes = m
+    names = [f"t{i}" for i in range(len(sizes))]
+    for nm, n, a in zip(names, sizes, dense):
+        data[nm].num_nodes = n
+        idx = a.nonzero().t().contiguous()                         # [2, E]: (patient, type)
+        data["patient", "has_" + nm, nm].edge_index = idx.to(dev)
+        data[nm, "has_" + nm + "_rev", "patient"].edge_index = idx.flip(0).contiguous().to(dev)
+    gi = G.GraphIndex(data)
+    pb = gi.hub_bits("patient")
+    assert pb is not None and pb.types == names
+    assert pb.bits_out is pb.bits_in, "flip(0) reverse relations must share one bit matrix"
+    return dense, pb
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,sizes,density", [(128, [50, 200, 100], [0.2, 0.01, 0.03]), (1000, [20, 30, 25], [0.5, 0.2, 0.3]),
+                                             (4099, [160, 200, 100], [0.67, 0.05, 0.28]), (70001, [50, 200, 100], [0.4, 0.01, 0.05]),
+                                             (777, [5, 5, 5, 40], [0.5, 0.5, 0.5, 0.1]), (300, [300], [0.1])])
+def test_layer_fwd_tc(m, sizes, density, pkg):
+    G, ops, _, _, L = _mods()
+    dev = torch.device("cuda:0")
+    dense, pb = _random_hub(G, m, sizes, density, dev, seed=m)
+    d = 128
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(m, d, generator=gen)
+    w = torch.randn(d, d, generator=gen) / d ** 0.5
+    w2 = torch.randn(d, d, generator=gen) / d ** 0.5
+    b1, b2 = torch.randn(d, generator=gen), torch.randn(d, generator=gen)
+    ys = [torch.randn(n, d, generator=gen) for n in sizes]
+    rs = [1.0 / a.sum(1).clamp(min=1) for a in dense]
+    # library result
+    wcat, bias = ops.layer_cat_weights_([w.to(dev), w2.to(dev)], False, [y.to(dev) for y in ys], [None] * len(sizes), pb.offs, d,
+                                        d + 32 * pb.nw, d, [b1.to(dev), b2.to(dev)])
+    torch.testing.assert_close(bias.cpu(), b1 + b2)
+    assert torch.equal(wcat[:, :d].cpu(), w + w2)
+    for y, off, n in zip(ys, pb.offs, sizes):
+        assert torch.equal(wcat[:, d + off:d + off + n].cpu(), y.t())
+    rs_lib = pb.rscale_in()
+    for a, b in zip(rs_lib, rs):
+        torch.testing.assert_close(a.cpu(), b, rtol=0, atol=0)
+    out = torch.full((m, d), float("nan"), device=dev)
+    sums = torch.zeros(2 * d, dtype=torch.float64, device=dev)
+    ops.layer_fwd_tc_(x.to(dev), wcat, bias, pb.bits_in, pb, rs_lib, out, sums)
+    torch.cuda.synchronize()
+    # references
+    ref = x.double() @ (w + w2).double().t() + (b1 + b2).double()
+    ref_t = tf32_trunc(x).double() @ tf32_trunc(w + w2).double().t() + (b1 + b2).double()
+    for a, r, y in zip(dense, rs, ys):
+        ref += (a.double() * r.double()[:, None]) @ y.double()
+        ref_t += (a.double() * tf32_trunc(r).double()[:, None]) @ tf32_trunc(y).double()
+    assert torch.isfinite(out).all()
+    assert relmax(out, ref_t) < 2e-5, "tcgen05 result differs from the TF32-truncated float64 product"
+    assert relmax(out, ref) < 3e-3
+    # BatchNorm column statistics from the epilogue
+    o64 = out.double().cpu()
+    torch.testing.assert_close(sums[:d].cpu(), o64.sum(0), rtol=1e-6, atol=1e-6 * m)
+    torch.testing.assert_close(sums[d:].cpu(), (o64 * o64).sum(0), rtol=1e-6, atol=1e-6 * m)
+    # deterministic
+    out2 = torch.empty_like(out)
+    ops.layer_fwd_tc_(x.to(dev), wcat, bias, pb.bits_in, pb, rs_lib, out2)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,sizes,density", [(32, [50, 200, 100], [0.2, 0.01, 0.03]), (1000, [20, 30, 25], [0.5, 0.2, 0.3]),
+                                             (4099, [160, 200, 100], [0.67, 0.05, 0.28]), (70001, [50, 200, 100], [0.4, 0.01, 0.05]),
+                                             (777, [5, 5, 5, 40], [0.5, 0.5, 0.5, 0.1]), (5000, [300], [0.1])])
+def test_layer_adjT_tc(m, sizes, density, pkg):
+    G, ops, _, _, L = _mods()
+    dev = torch.device("cuda:0")
+    dense, pb = _random_hub(G, m, sizes, density, dev, seed=m + 1)
+    d = 128
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(m, d, generator=gen)
+    xt = tf32_trunc(x).double()
+    # forward use: column scale = 1/deg of the type node, no row scale
+    out = ops.layer_adjT_tc_(x.to(dev), pb.bits_out, pb, [None] * len(sizes), pb.col_scale_out())
+    torch.cuda.synchronize()
+    assert out.shape == (32 * pb.nw, d)
+    covered = torch.zeros(32 * pb.nw, dtype=torch.bool)
+    for a, off, n in zip(dense, pb.offs, sizes):
+        cs = 1.0 / a.sum(0).clamp(min=1)
+        ref_t = (a.double().t() @ xt) * cs.double()[:, None]
+        ref = (a.double().t() @ x.double()) * cs.double()[:, None]
+        got = out[off:off + n]
+        assert relmax(got, ref_t) < 2e-5
+        assert relmax(got, ref) < 3e-3
+        covered[off:off + n] = True
+    assert float(out.cpu()[~covered].abs().max() if (~covered).any() else 0.0) == 0.0, "padding columns must stay zero"
+    # backward use: row scale = 1/deg of the patient per relation, no column scale
+    rs = pb.rscale_in()
+    out = ops.layer_adjT_tc_(x.to(dev), pb.bits_in, pb, rs, None)
+    for a, r, off, n in zip(dense, rs, pb.offs, sizes):
+        ref_t = (a.double() * tf32_trunc(r.cpu()).double()[:, None]).t() @ xt
+        assert relmax(out[off:off + n], ref_t) < 2e-5
+    out2 = ops.layer_adjT_tc_(x.to(dev), pb.bits_in, pb, rs, None)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec_name,n_p", [("tiny", 2000), ("C1", 1834), ("C2", 6000)])
+def test_fused_layer_equals_per_relation_path(spec_name, n_p, pkg):
+    """model._layer through PatientSideFn (bit adjacency, 2 + 3 launches) vs the per-relation path of round 1, forward and
+    backward, and both against the exact-fp32 kernels (which are pinned to the reference's golden vectors)."""
+    G, ops, M, S, L = _mods()
+    dev = torch.device("cuda:0")
+    base = S.SPECS[spec_name]
+    scale = n_p / base.n_patient
+    spec = S.GraphSpec("t", n_p, base.n_lab, base.n_dx, base.n_med, int(base.e_lab * scale), int(base.e_dx * scale), int(base.e_med * scale),
+                       base.low_degree_frac)
+    g = S.make_graph(spec, seed=5).to(dev)
+    cfg = {"model": {"architecture": "RGCN", "hidden_dim": 128, "num_layers": 2, "dropout": 0.0, "use_batch_norm": True, "activation": "relu"}}
+    torch.manual_seed(0)
+    model = M.build_model(cfg, (g.node_types, g.edge_types), None).to(dev)
+    model._init_embeddings(g)
+    model.train()
+    gi = model._graph_index(g)
+    gen = torch.Generator(device=dev).manual_seed(3)
+    counts = {nt: int(g[nt].num_nodes) for nt in g.node_types}
+    x0 = {nt: torch.randn(n, 128, device=dev, generator=gen) for nt, n in counts.items()}
+    gout = {nt: torch.randn(n, 128, device=dev, generator=gen) for nt, n in counts.items()}
+    params = list(model.convs[0].parameters())
+
+    def run(mode, fused):
+        ops.set_precision(mode)
+        saved = M.HeteroRGCN._layer_fused
+        if not fused:
+            M.HeteroRGCN._layer_fused = lambda self, *a, **k: None
+        try:
+            x = {nt: v.clone().requires_grad_(True) for nt, v in x0.items()}
+            for p in params:
+                p.grad = None
+            out = model._layer(0, x, gi)
+            torch.autograd.backward([out[nt] for nt in out], [gout[nt] for nt in out])
+            res = {"out." + nt: out[nt].detach().clone() for nt in out}
+            res.update({"dx." + nt: x[nt].grad.clone() for nt in x})
+            res.update({"dp.%d" % i: p.grad.clone() for i, p in enumerate(params)})
+            return res
+        finally:
+            M.HeteroRGCN._layer_fused = saved
+
+    old = ops.PRECISION
+    try:
+        exact = run("fp32", False)
+        launches0 = L.load().b2g_launch_count()
+        fused = run("tf32", True)
+        n_fused = L.load().b2g_launch_count() - launches0
+        launches0 = L.load().b2g_launch_count()
+        unfused = run("tf32", False)
+        n_unfused = L.load().b2g_launch_count() - launches0
+    finally:
+        ops.set_precision(old)
+    assert set(exact) == set(fused) == set(unfused)
+    assert n_fused < n_unfused, f"the fused layer should need fewer launches ({n_fused} vs {n_unfused})"
+    for k in exact:
+        e_f, e_u = relmax(fused[k], exact[k]), relmax(unfused[k], exact[k])
+        assert e_f < 5e-3, f"{k}: fused tf32 vs exact fp32 {e_f:.2e}"
+        assert e_u < 5e-3, f"{k}: per-relation tf32 vs exact fp32 {e_u:.2e}"
