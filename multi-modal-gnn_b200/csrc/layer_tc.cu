@@ -17,14 +17,14 @@
 // HBM traffic per patient row: forward 512 B (x_p) + 512 B (out_p) + bits; the reduction operands (W_root | Y, 128 x K fp32)
 // stream from L2 one 32-column chunk at a time next to the matching A chunk.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 using namespace b2g;
 
 constexpr int LY_MAXW = 24;                      // adjacency words per patient row (<= 768 type nodes over all relations)
 constexpr int LY_MAXREL = 4;
-constexpr int LY_THREADS = 384;                  // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue, 8-11 expanders
-constexpr int LY_EXP_WARPS = 4;
+constexpr int LY_THREADS = 384;                  // warps: 0 TMA, 1 MMA, 4-7 epilogue, 2-3 and 8-11 expanders (2 also owns TMEM)
 constexpr int LY_MAX_STAGES = 6;
 constexpr int A_CHUNK = TILE_M * KB * 4;         // [128 rows x 128 B] = 16 KB
 constexpr int STG_ROW = 128 + 16;                // epilogue staging row: 32 floats + 16 B pad (conflict-free 16-byte accesses)
@@ -53,18 +53,30 @@ struct LayerParams {
   int kx;                              // dense reduction columns (x), multiple of 32 (may be 0)
   int tmem_cols;
   int stages;
+  long long* dbg_out;                  // diagnosis only (dbg & 8): per-role wait cycles of CTA 0
+  int dbg;                             // diagnosis only (B2G_LAYER_DBG): 1 = skip the bit expansion, 2 = skip the B loads, 4 = skip x loads
 };
+
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
+  if (on) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
 
 __device__ __forceinline__ float pick_scale(const float (&s)[LY_MAXREL], int r) {
   return r == 0 ? s[0] : (r == 1 ? s[1] : (r == 2 ? s[2] : s[3]));
 }
 // 4 consecutive adjacency entries (bits b0 .. b0+3 of `word`) as {0 | scale}
 __device__ __forceinline__ uint4 expand4(uint32_t word, int b0, uint32_t sbits) {
-  uint4 v;
-  v.x = (0u - ((word >> b0) & 1u)) & sbits;
-  v.y = (0u - ((word >> (b0 + 1)) & 1u)) & sbits;
-  v.z = (0u - ((word >> (b0 + 2)) & 1u)) & sbits;
-  v.w = (0u - ((word >> (b0 + 3)) & 1u)) & sbits;
+  uint4 v;                                                   // (one LOP3 with predicate output + one SEL per element)
+  v.x = (word & (1u << b0)) ? sbits : 0u;
+  v.y = (word & (2u << b0)) ? sbits : 0u;
+  v.z = (word & (4u << b0)) ? sbits : 0u;
+  v.w = (word & (8u << b0)) ? sbits : 0u;
   return v;
 }
 
@@ -76,8 +88,11 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
   __shared__ __align__(8) uint64_t bar_full[LY_MAX_STAGES], bar_empty[LY_MAX_STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ double s_stat[4][2][32];
+  __shared__ uint4 s_lut[16];                          // nibble -> four {0 | ~0} masks
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 16)
+    s_lut[threadIdx.x] = make_uint4((threadIdx.x & 1) ? ~0u : 0u, (threadIdx.x & 2) ? ~0u : 0u, (threadIdx.x & 4) ? ~0u : 0u, (threadIdx.x & 8) ? ~0u : 0u);
   const int nxc = prm.kx / KB;                         // chunks fed by TMA from x
   const int nw = prm.bl.nw;
   const int nc = nxc + nw;                             // chunks per tile
@@ -87,10 +102,13 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
   uint8_t* smem_stg = base + (size_t)prm.stages * stage_bytes;
   const int64_t n_tiles = (prm.m + TILE_M - 1) / TILE_M;
   const int nst = prm.stages;
+  const bool tm = (prm.dbg & 8) && blockIdx.x == 0;
+  long long w0 = 0, w1 = 0;
+  const long long t_begin = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < LY_MAX_STAGES; ++s) {
-      mbar_init(&bar_full[s], 1 + LY_EXP_WARPS);       // TMA producer (expect_tx) + one arrive per expander warp
+      mbar_init(&bar_full[s], 2);                      // TMA producer (expect_tx) + the stage's expander warp
       mbar_init(&bar_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -111,101 +129,123 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
   if (warp == 0) {
     // ===== TMA producer: per chunk the B columns (W_root | Y), and for the first kx/32 chunks the x columns =====
     if (elect_one()) {
-      uint32_t g = 0;
+      int s = 0;
+      uint32_t ph = 1;                                 // parity to wait for on bar_empty (the first pass over the ring is free)
       for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        for (int c = 0; c < nc; ++c, ++g) {
-          const int s = g % nst;
-          const uint32_t ph = (g / nst) & 1;
-          mbar_wait(&bar_empty[s], ph ^ 1);
+        for (int c = 0; c < nc; ++c) {
+          mbar_wait_t(&bar_empty[s], ph, w0, tm);
           uint8_t* st = base + (size_t)s * stage_bytes;
-          mbar_expect_tx(&bar_full[s], b_bytes + (c < nxc ? (uint32_t)A_CHUNK : 0u));
-          tma_load_2d(st + A_CHUNK, &map_w, &bar_full[s], c * KB, 0);
-          if (c < nxc) tma_load_2d(st, &map_x, &bar_full[s], c * KB, (int)(t * TILE_M));
+          const bool ldb = !(prm.dbg & 2), ldx = c < nxc && !(prm.dbg & 4);
+          mbar_expect_tx(&bar_full[s], (ldb ? b_bytes : 0u) + (ldx ? (uint32_t)A_CHUNK : 0u));
+          if (ldb) tma_load_2d(st + A_CHUNK, &map_w, &bar_full[s], c * KB, 0);
+          if (ldx) tma_load_2d(st, &map_x, &bar_full[s], c * KB, (int)(t * TILE_M));
+          if (++s == nst) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc(prm.n);
-    uint32_t g = 0;
-    int it = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int a = it & 1;
-      const uint32_t pa = (it >> 1) & 1;
-      mbar_wait(&bar_tempty[a], pa ^ 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_tmem = tmem_base + (uint32_t)(a * prm.n);
-      for (int c = 0; c < nc; ++c, ++g) {
-        const int s = g % nst;
-        const uint32_t ph = (g / nst) & 1;
-        mbar_wait(&bar_full[s], ph);
+    // ===== MMA issuer: ONE thread runs the whole loop; stage / phase counters are incremental and the shared-memory
+    // descriptors are formed by adding the stage offset to a descriptor with a zero start address =====
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(prm.n);
+      const uint64_t dhi = make_desc(0);
+      const uint32_t base16 = smem_u32(base) >> 4, st16 = stage_bytes >> 4, a16 = A_CHUNK >> 4;
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int a = it & 1;
+        mbar_wait_t(&bar_tempty[a], ((it >> 1) & 1) ^ 1, w1, tm);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + A_CHUNK;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * prm.n);
+        for (int c = 0; c < nc; ++c) {
+          mbar_wait_t(&bar_full[s], ph, w0, tm);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = dhi + (base16 + (uint32_t)s * st16);
+          const uint64_t db = da + a16;
 #pragma unroll
-          for (int k8 = 0; k8 < KB / 8; ++k8)
-            umma_tf32(d_tmem, make_desc(sa + k8 * 32), make_desc(sb + k8 * 32), idesc, (c | k8) != 0);
+          for (int k8 = 0; k8 < KB / 8; ++k8) umma_tf32(d_tmem, da + 2 * k8, db + 2 * k8, idesc, (c | k8) != 0);
           umma_commit(&bar_empty[s]);
           if (c == nc - 1) umma_commit(&bar_tfull[a]);
+          if (++s == nst) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp == 2 || warp == 3 || warp >= 8) {
     // ===== expanders: adjacency bits -> TF32 A chunks (K-major SWIZZLE_128B: 16-byte chunk j of row r at j ^ (r & 7)) =====
-    const int r = (warp - 8) * 32 + lane;              // tile row owned by this lane
-    uint32_t wcur[LY_MAXW], wnxt[LY_MAXW];
-    float scur[LY_MAXREL], snxt[LY_MAXREL];
-    auto load_row = [&](int64_t t, uint32_t (&w)[LY_MAXW], float (&sc)[LY_MAXREL]) {
-      const int64_t row = t * TILE_M + r;
-      const bool live = t < n_tiles && row < prm.m;
+    // Expander warp e is bound to pipeline stage e: it handles every chunk g = e (mod stages) -- all 128 rows of the chunk,
+    // 4 rows per lane -- so up to `stages` chunks are being expanded at the same time, and it sees every phase of its stage's
+    // barriers in order (a warp that skipped phases could not use parity waits).  A nibble of the word indexes a 16-entry
+    // look-up table of four {0 | ~0} masks (one LDS.128 instead of ~12 ALU instructions per 4 entries).
+    // For an x chunk there is nothing to expand: the warp only contributes the stage's second arrival.
+    const int e = warp >= 8 ? warp - 6 : warp - 2;     // 0..5
+    if (e < nst) {
+      const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const uint32_t total = (uint32_t)(my_tiles * nc);
+      uint32_t wn[4], san[4], sbn[4];
+      int cn = e % nc;                                 // chunk-in-tile and tile counter of the chunk being prefetched
+      int64_t tn = blockIdx.x + (int64_t)(e / nc) * gridDim.x;
+      auto prefetch = [&](uint32_t g) {                // words + row scales of chunk g (if it is an adjacency chunk)
+        if (g >= total || cn < nxc) return;
+        const int k = cn - nxc;
+        const float* ra = prm.rscale[prm.bl.rel_a[k]];
+        const float* rb = prm.rscale[prm.bl.rel_b[k]];
 #pragma unroll
-      for (int k = 0; k < LY_MAXW; ++k) w[k] = (live && k < nw) ? __ldg(prm.bits + (size_t)row * nw + k) : 0u;
+        for (int i = 0; i < 4; ++i) {
+          const int64_t row = tn * TILE_M + i * 32 + lane;
+          const bool live = row < prm.m;
+          wn[i] = live ? __ldg(prm.bits + (size_t)row * nw + k) : 0u;
+          san[i] = (live && ra) ? __float_as_uint(__ldg(ra + row)) : 0x3f800000u;
+          sbn[i] = (live && rb) ? __float_as_uint(__ldg(rb + row)) : 0x3f800000u;
+        }
+      };
+      prefetch((uint32_t)e);
+      uint32_t ph = 1;                                 // parity to wait for on bar_empty[e]
+      for (uint32_t g = (uint32_t)e; g < total; g += (uint32_t)nst, ph ^= 1) {
+        const int c = cn;
+        uint32_t wc[4], sac[4], sbc[4];
 #pragma unroll
-      for (int q = 0; q < LY_MAXREL; ++q) sc[q] = (live && prm.rscale[q]) ? __ldg(prm.rscale[q] + row) : 1.0f;
-    };
-    load_row(blockIdx.x, wcur, scur);
-    uint32_t g = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      load_row(t + gridDim.x, wnxt, snxt);             // next tile's words: in flight during this tile's expansion
-      for (int c = 0; c < nxc; ++c, ++g) {             // x chunks: nothing to write, but keep the arrival count uniform
-        const int s = g % nst;
-        mbar_wait(&bar_empty[s], ((g / nst) & 1) ^ 1);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_full[s]);
-      }
-#pragma unroll
-      for (int k = 0; k < LY_MAXW; ++k) {
-        if (k < nw) {
-          const int s = g % nst;
-          mbar_wait(&bar_empty[s], ((g / nst) & 1) ^ 1);
-          uint8_t* arow = base + (size_t)s * stage_bytes + r * 128;
-          const uint32_t word = wcur[k];
+        for (int i = 0; i < 4; ++i) { wc[i] = wn[i]; sac[i] = san[i]; sbc[i] = sbn[i]; }
+        cn += nst;                                     // advance (cn, tn) to chunk g + stages
+        while (cn >= nc) { cn -= nc; tn += gridDim.x; }
+        prefetch(g + (uint32_t)nst);
+        mbar_wait_t(&bar_empty[e], ph, w0, tm);
+        if (c >= nxc && !(prm.dbg & 1)) {
+          const int k = c - nxc;
+          uint8_t* abase = base + (size_t)e * stage_bytes;
           const int split = prm.bl.split[k];
-          const uint32_t sa = __float_as_uint(pick_scale(scur, prm.bl.rel_a[k]));
           if (split >= 32) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) = expand4(word, 4 * j, sa);
-          } else {
-            const uint32_t sb = __float_as_uint(pick_scale(scur, prm.bl.rel_b[k]));
-            const uint32_t lo = word & ((1u << split) - 1u), hi = word & ~((1u << split) - 1u);
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 32 + lane;
+              uint8_t* arow = abase + r * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 va = expand4(lo, 4 * j, sa), vb = expand4(hi, 4 * j, sb);
-              *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) = make_uint4(va.x | vb.x, va.y | vb.y, va.z | vb.z, va.w | vb.w);
+              for (int j = 0; j < 8; ++j) {
+                uint4 m4 = s_lut[(wc[i] >> (4 * j)) & 15u];
+                m4.x &= sac[i]; m4.y &= sac[i]; m4.z &= sac[i]; m4.w &= sac[i];
+                *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) = m4;
+              }
+            }
+          } else {
+            const uint32_t msk = (1u << split) - 1u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 32 + lane;
+              uint8_t* arow = abase + r * 128;
+              const uint32_t lo = wc[i] & msk, hi = wc[i] & ~msk;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 ma = s_lut[(lo >> (4 * j)) & 15u], mb = s_lut[(hi >> (4 * j)) & 15u];
+                *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) =
+                    make_uint4((ma.x & sac[i]) | (mb.x & sbc[i]), (ma.y & sac[i]) | (mb.y & sbc[i]), (ma.z & sac[i]) | (mb.z & sbc[i]),
+                               (ma.w & sac[i]) | (mb.w & sbc[i]));
+              }
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_full[s]);
-          ++g;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[e]);
       }
-#pragma unroll
-      for (int k = 0; k < LY_MAXW; ++k) wcur[k] = wnxt[k];
-#pragma unroll
-      for (int q = 0; q < LY_MAXREL; ++q) scur[q] = snxt[q];
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> staging tile -> coalesced 16-byte stores (+ bias, + BatchNorm column sums) =====
@@ -220,7 +260,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(&bar_tfull[s], ph);
+      mbar_wait_t(&bar_tfull[s], ph, w0, tm);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row0 = t * TILE_M + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * prm.n);
@@ -293,6 +333,11 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
       }
     }
   }
+  if (tm && lane == 0) {
+    prm.dbg_out[warp * 4 + 0] = w0;
+    prm.dbg_out[warp * 4 + 1] = w1;
+    prm.dbg_out[warp * 4 + 2] = clock64() - t_begin;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
@@ -305,10 +350,11 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
 // operands use the 32-byte-atom flavour of the 128-byte swizzle (dense_tc.cu: k_wgrad_tf32): a sub-tile is [rows x 128 B]
 // (32 columns), the 32-byte chunk j of row r sits at chunk j ^ (r & 3); SBO = 512 B (4 rows), LBO = one sub-tile.
 constexpr int AT_THREADS = 512;                  // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue, 8-15 expanders
-constexpr int AT_EXP_WARPS = 8;
 constexpr int AT_ROWS = 32;                      // reduction rows per stage
 constexpr int AT_SUB = AT_ROWS * KB * 4;         // 4 KB sub-tile
-constexpr int AT_MAX_STAGES = 6;
+constexpr int AT_BSTAGES = 2;                    // ring of expanded adjacency stages (nw x 4 KB each)
+constexpr int AT_GROUP = 4;                      // expander warps per adjacency stage: group gi = stage, warp j = words j, j+4, ...
+constexpr int AT_MAX_XSTAGES = 10;               // ring of X stages (16 KB each): deep, so that enough HBM bytes are in flight
 
 struct AdjTParams {
   const uint32_t* bits;
@@ -316,9 +362,10 @@ struct AdjTParams {
   BitLayout bl;
   float* partial;                      // [grid][128][nb]
   int64_t m;
-  int nb;                              // 32 * nw
+  int nb;                              // 32 * (nw + ones)
   int tmem_cols;
-  int stages;
+  int xstages;
+  int ones;                            // 1: one more 32-column block whose first column is 1 -> row 32 nw of the output = column sums of X
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn32(uint32_t smem_addr) {
@@ -331,23 +378,42 @@ __device__ __forceinline__ uint64_t make_desc_mn32(uint32_t smem_addr) {
   return d;
 }
 
+// dynamic smem (1024-byte aligned): X ring [xstages][4 sub-tiles x 4 KB] | adjacency ring [2][nw sub-tiles x 4 KB]
 __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_constant__ CUtensorMap map_x,
                                                              const __grid_constant__ AdjTParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[AT_MAX_STAGES], bar_empty[AT_MAX_STAGES], bar_done;
+  __shared__ __align__(8) uint64_t bar_xfull[AT_MAX_XSTAGES], bar_xempty[AT_MAX_XSTAGES], bar_bfull[AT_BSTAGES], bar_bempty[AT_BSTAGES],
+      bar_done;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = prm.bl.nw;
   const uint32_t a_bytes = 4u * AT_SUB;                                // 128 columns of X
-  const uint32_t stage_bytes = a_bytes + (uint32_t)nw * AT_SUB;
+  const uint32_t b_bytes = (uint32_t)(nw + prm.ones) * AT_SUB;
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  uint8_t* bbase = base + (size_t)prm.xstages * a_bytes;
+  if (prm.ones && warp == 3) {
+    // constant block: element (row r, column 0) = 1 (32-byte chunk 0 of row r sits at chunk r & 3), everything else 0.
+    // Rows beyond m contribute nothing: TMA zero-fills the matching X rows.
+    for (int sgi = 0; sgi < AT_BSTAGES; ++sgi) {
+      uint32_t* sub = reinterpret_cast<uint32_t*>(bbase + (size_t)sgi * b_bytes + (size_t)nw * AT_SUB);
+      for (int i = lane; i < AT_SUB / 4; i += 32) {
+        const int r = i >> 5, w = i & 31;
+        sub[i] = (w == ((r & 3) << 3)) ? 0x3f800000u : 0u;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   const int64_t n_tiles = (prm.m + AT_ROWS - 1) / AT_ROWS;
-  const int nst = prm.stages;
+  const int nxs = prm.xstages;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < AT_MAX_STAGES; ++s) {
-      mbar_init(&bar_full[s], 1 + AT_EXP_WARPS);
-      mbar_init(&bar_empty[s], 1);
+    for (int s = 0; s < AT_MAX_XSTAGES; ++s) {
+      mbar_init(&bar_xfull[s], 1);
+      mbar_init(&bar_xempty[s], 1);
+    }
+    for (int s = 0; s < AT_BSTAGES; ++s) {
+      mbar_init(&bar_bfull[s], AT_GROUP);
+      mbar_init(&bar_bempty[s], 1);
     }
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -363,89 +429,108 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
 
   if (warp == 0) {
     if (elect_one()) {
-      uint32_t it = 0;
-      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int s = it % nst;
-        mbar_wait(&bar_empty[s], ((it / nst) & 1) ^ 1);
-        mbar_expect_tx(&bar_full[s], a_bytes);
-        uint8_t* st = base + (size_t)s * stage_bytes;
-        for (int c = 0; c < 4; ++c) tma_load_2d(st + c * AT_SUB, &map_x, &bar_full[s], c * KB, (int)(t * AT_ROWS));
+      int s = 0;
+      uint32_t ph = 1;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(&bar_xempty[s], ph);
+        mbar_expect_tx(&bar_xfull[s], a_bytes);
+        uint8_t* st = base + (size_t)s * a_bytes;
+        for (int c = 0; c < 4; ++c) tma_load_2d(st + c * AT_SUB, &map_x, &bar_xfull[s], c * KB, (int)(t * AT_ROWS));
+        if (++s == nxs) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // D rows = the 128 columns of X; N is split into pieces of <= 256 columns, one MMA each per 8 reduction rows
-    const int n1 = prm.nb > 256 ? 256 : prm.nb, n2 = prm.nb - n1;
-    const uint32_t idesc1 = make_idesc(n1) | (1u << 15) | (1u << 16);
-    const uint32_t idesc2 = make_idesc(n2 > 0 ? n2 : 8) | (1u << 15) | (1u << 16);
-    uint32_t it = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int s = it % nst;
-      mbar_wait(&bar_full[s], (it / nst) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + a_bytes;
+    // D rows = the 128 columns of X; N is split into pieces of <= 256 columns, one MMA each per 8 reduction rows.
+    // One thread runs the loop; stage / phase counters are incremental and descriptors are formed by addition.
+    if (elect_one()) {
+      const int n1 = prm.nb > 256 ? 256 : prm.nb, n2 = prm.nb - n1;
+      const uint32_t idesc1 = make_idesc(n1) | (1u << 15) | (1u << 16);
+      const uint32_t idesc2 = make_idesc(n2 > 0 ? n2 : 16) | (1u << 15) | (1u << 16);
+      const uint64_t dhi = make_desc_mn32(0);
+      const uint32_t xa = smem_u32(base) >> 4, ba = smem_u32(bbase) >> 4;
+      const uint32_t a16 = a_bytes >> 4, b16 = b_bytes >> 4;
+      int sx = 0, sb_ = 0;
+      uint32_t phx = 0, phb = 0;
+      bool first = true;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(&bar_xfull[sx], phx);
+        mbar_wait(&bar_bfull[sb_], phb);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = dhi + (xa + (uint32_t)sx * a16);
+        const uint64_t db = dhi + (ba + (uint32_t)sb_ * b16);
 #pragma unroll
-        for (int j = 0; j < AT_ROWS / 8; ++j) {
-          umma_tf32(tmem_base, make_desc_mn32(sa + j * 1024), make_desc_mn32(sb + j * 1024), idesc1, (it | j) != 0);
-          if (n2 > 0)
-            umma_tf32(tmem_base + 256, make_desc_mn32(sa + j * 1024), make_desc_mn32(sb + 8 * AT_SUB + j * 1024), idesc2, (it | j) != 0);
+        for (int j = 0; j < AT_ROWS / 8; ++j) {          // 8 reduction rows = 1024 B = 64 descriptor units
+          umma_tf32(tmem_base, da + 64 * j, db + 64 * j, idesc1, !(first && j == 0));
+          if (n2 > 0) umma_tf32(tmem_base + 256, da + 64 * j, db + (8 * AT_SUB >> 4) + 64 * j, idesc2, !(first && j == 0));
         }
-        umma_commit(&bar_empty[s]);
+        first = false;
+        umma_commit(&bar_xempty[sx]);
+        umma_commit(&bar_bempty[sb_]);
+        if (++sx == nxs) { sx = 0; phx ^= 1; }
+        if (++sb_ == AT_BSTAGES) { sb_ = 0; phb ^= 1; }
       }
-      __syncwarp();
+      umma_commit(&bar_done);
     }
-    if (elect_one()) umma_commit(&bar_done);
-    __syncwarp();
   } else if (warp >= 8) {
-    // expander warp e owns words e, e + 8, e + 16 of all 32 rows of a stage (lane = row)
-    const int e = warp - 8;
-    constexpr int WPE = LY_MAXW / AT_EXP_WARPS;        // words per expander warp (3)
+    // expander group gi (4 warps) owns adjacency stage gi, i.e. the tiles it = gi, gi + 2, ...; inside the group warp j expands
+    // the words j, j + 4, ... of the stage's 32 rows (lane = row): two stages are being expanded at any time
+    const int gi = (warp - 8) / AT_GROUP, j4 = (warp - 8) % AT_GROUP;
+    constexpr int WPE = LY_MAXW / AT_GROUP;            // words per expander warp (6)
     uint32_t wcur[WPE], wnxt[WPE];
     float scur[LY_MAXREL], snxt[LY_MAXREL];
+    const int64_t tstep = (int64_t)gridDim.x * AT_BSTAGES;
     auto load_row = [&](int64_t t, uint32_t (&w)[WPE], float (&sc)[LY_MAXREL]) {
       const int64_t row = t * AT_ROWS + lane;
       const bool live = t < n_tiles && row < prm.m;
 #pragma unroll
       for (int i = 0; i < WPE; ++i) {
-        const int k = e + i * AT_EXP_WARPS;
+        const int k = j4 + i * AT_GROUP;
         w[i] = (live && k < nw) ? __ldg(prm.bits + (size_t)row * nw + k) : 0u;
       }
 #pragma unroll
       for (int q = 0; q < LY_MAXREL; ++q) sc[q] = (live && prm.rscale[q]) ? __ldg(prm.rscale[q] + row) : 1.0f;
     };
-    load_row(blockIdx.x, wcur, scur);
-    uint32_t it = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      load_row(t + gridDim.x, wnxt, snxt);
-      const int s = it % nst;
-      mbar_wait(&bar_empty[s], ((it / nst) & 1) ^ 1);
-      uint8_t* bst = base + (size_t)s * stage_bytes + a_bytes;
+    const int64_t t_first = blockIdx.x + (int64_t)gi * gridDim.x;
+    load_row(t_first, wcur, scur);
+    uint32_t u = 0;                                    // use count of this group's stage
+    for (int64_t t = t_first; t < n_tiles; t += tstep, ++u) {
+      load_row(t + tstep, wnxt, snxt);
+      mbar_wait(&bar_bempty[gi], (u & 1) ^ 1);
+      uint8_t* bst = bbase + (size_t)gi * b_bytes;
 #pragma unroll
       for (int i = 0; i < WPE; ++i) {
-        const int k = e + i * AT_EXP_WARPS;
+        const int k = j4 + i * AT_GROUP;
         if (k < nw) {
           uint8_t* brow = bst + (size_t)k * AT_SUB + lane * 128;
           const uint32_t word = wcur[i];
           const int split = prm.bl.split[k];
           const uint32_t sa = __float_as_uint(pick_scale(scur, prm.bl.rel_a[k]));
-          const uint32_t sb = __float_as_uint(pick_scale(scur, prm.bl.rel_b[k]));
-          const uint32_t msk = split >= 32 ? 0xffffffffu : ((1u << split) - 1u);
-          const uint32_t lo = word & msk, hi = word & ~msk;
+          if (split >= 32) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {                  // 32-byte chunk j (8 columns) at chunk j ^ (row & 3)
-            uint8_t* dst = brow + ((j ^ (lane & 3)) << 5);
+            for (int j = 0; j < 4; ++j) {                // 32-byte chunk j (8 columns) at chunk j ^ (row & 3)
+              uint8_t* dst = brow + ((j ^ (lane & 3)) << 5);
+              *reinterpret_cast<uint4*>(dst) = expand4(word, 8 * j, sa);
+              *reinterpret_cast<uint4*>(dst + 16) = expand4(word, 8 * j + 4, sa);
+            }
+          } else {
+            const uint32_t sb = __float_as_uint(pick_scale(scur, prm.bl.rel_b[k]));
+            const uint32_t msk = (1u << split) - 1u;
+            const uint32_t lo = word & msk, hi = word & ~msk;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint4 va = expand4(lo, 8 * j + 4 * h, sa), vb = expand4(hi, 8 * j + 4 * h, sb);
-              *reinterpret_cast<uint4*>(dst + 16 * h) = make_uint4(va.x | vb.x, va.y | vb.y, va.z | vb.z, va.w | vb.w);
+            for (int j = 0; j < 4; ++j) {
+              uint8_t* dst = brow + ((j ^ (lane & 3)) << 5);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint4 va = expand4(lo, 8 * j + 4 * h, sa), vb = expand4(hi, 8 * j + 4 * h, sb);
+                *reinterpret_cast<uint4*>(dst + 16 * h) = make_uint4(va.x | vb.x, va.y | vb.y, va.z | vb.z, va.w | vb.w);
+              }
             }
           }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_full[s]);
+      if (lane == 0) mbar_arrive(&bar_bfull[gi]);
 #pragma unroll
       for (int i = 0; i < WPE; ++i) wcur[i] = wnxt[i];
 #pragma unroll
@@ -663,6 +748,12 @@ extern "C" int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* 
   while (cols < 2 * n) cols <<= 1;
   prm.tmem_cols = cols;
   prm.stages = layer_stages(n);
+  {
+    const char* e = getenv("B2G_LAYER_DBG");
+    prm.dbg = e ? atoi(e) : 0;
+    const char* es = getenv("B2G_LAYER_STAGES");
+    if (es && atoi(es) >= 2 && atoi(es) <= prm.stages) prm.stages = atoi(es);
+  }
   int64_t tiles = ceil_div(m, TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   prm.stats = nullptr;
@@ -680,8 +771,21 @@ extern "C" int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* 
     B2G_CUDA(cudaFuncSetAttribute(k_layer_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
+  static long long* dbg_buf = nullptr;
+  if (prm.dbg & 8) {
+    if (!dbg_buf) B2G_CUDA(cudaMalloc(&dbg_buf, 64 * sizeof(long long)));
+    B2G_CUDA(cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), st));
+    prm.dbg_out = dbg_buf;
+  }
   k_layer_tf32<<<grid, LY_THREADS, smem, st>>>(map_x, map_w, prm);
   B2G_LAUNCH_CHECK();
+  if (prm.dbg & 8) {
+    long long h[64];
+    B2G_CUDA(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
+    B2G_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "[k_layer_tf32 CTA0 cycles] total %lld | TMA wait-empty %lld | MMA wait-full %lld wait-tempty %lld | epi(w4) wait-tfull %lld | "
+            "exp(w8) wait-empty(adj) %lld wait-empty(x) %lld\n", h[0 * 4 + 2], h[0], h[1 * 4], h[1 * 4 + 1], h[4 * 4], h[8 * 4], h[8 * 4 + 1]);
+  }
   if (stat_sums) {
     k_stats_reduce<<<(unsigned)ceil_div(2 * n, 128), 128, 0, st>>>(prm.stats, grid, 2 * n, stat_sums);
     B2G_LAUNCH_CHECK();
@@ -689,23 +793,32 @@ extern "C" int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* 
   return B2G_OK;
 }
 
+namespace {
+inline int adjT_xstages(int nw) {
+  const size_t left = 224 * 1024 - (size_t)AT_BSTAGES * nw * AT_SUB;
+  int xs = (int)(left / (4 * (size_t)AT_SUB));
+  return xs > AT_MAX_XSTAGES ? AT_MAX_XSTAGES : xs;
+}
+}  // namespace
 extern "C" int b2g_layer_adjT_tc_supported(int64_t m, int d, int nw) {
   if (m < 1 || d != 128 || nw < 1 || nw > 16) return 0;        // D = [128, 32 nw] fp32 must fit the 512 TMEM columns
-  const size_t stage = 4 * (size_t)AT_SUB + (size_t)nw * AT_SUB;
-  return (226 * 1024) / stage >= 2 ? 1 : 0;
+  return adjT_xstages(nw) >= 2 ? 1 : 0;
 }
 extern "C" size_t b2g_layer_adjT_tc_ws_bytes(int nw) { return (size_t)sm_count() * 128 * 32 * nw * 4 + 256; }
 
 extern "C" int b2g_layer_adjT_tc(const float* x, const uint32_t* bits, const b2g_bit_layout_t* h_layout, const float* const* h_rscale,
-                                 const float* col_scale, int64_t m, float* out, void* ws, size_t ws_bytes, void* stream_) {
+                                 const float* col_scale, int64_t m, int with_colsum, float* out, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(x && bits && out && h_layout && b2g_layer_adjT_tc_supported(m, 128, h_layout->nw), "layer_adjT_tc: unsupported shape");
   B2G_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(ws) && (!col_scale || aligned16(col_scale)), "layer_adjT_tc: unaligned pointer");
   AdjTParams prm{};
   int rc = fill_layout(&prm.bl, h_layout);
   if (rc) return rc;
-  const int nw = prm.bl.nw, nb = 32 * nw;
-  if (!ws || ws_bytes < b2g_layer_adjT_tc_ws_bytes(nw)) {
+  const int nw = prm.bl.nw;
+  prm.ones = with_colsum ? 1 : 0;
+  B2G_CHECK_ARG(nw + prm.ones <= 16, "layer_adjT_tc: 32 (nw + 1) output columns exceed the 512 TMEM columns");
+  const int nb = 32 * (nw + prm.ones);
+  if (!ws || ws_bytes < b2g_layer_adjT_tc_ws_bytes(nw + prm.ones)) {
     set_error("layer_adjT_tc: workspace too small");
     return B2G_EWS;
   }
@@ -717,10 +830,9 @@ extern "C" int b2g_layer_adjT_tc(const float* x, const uint32_t* bits, const b2g
   int cols = 32;
   while (cols < nb) cols <<= 1;
   prm.tmem_cols = cols;
-  const size_t stage = 4 * (size_t)AT_SUB + (size_t)nw * AT_SUB;
-  prm.stages = (int)((226 * 1024) / stage);
-  if (prm.stages > AT_MAX_STAGES) prm.stages = AT_MAX_STAGES;
-  const size_t smem = (size_t)prm.stages * stage + 1024;
+  prm.xstages = adjT_xstages(nw + prm.ones);
+  B2G_CHECK_ARG(prm.xstages >= 2, "layer_adjT_tc: shared memory too small for nw=%d", nw);
+  const size_t smem = (size_t)prm.xstages * 4 * AT_SUB + (size_t)AT_BSTAGES * (nw + prm.ones) * AT_SUB + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     B2G_CUDA(cudaFuncSetAttribute(k_adjT_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -803,15 +803,17 @@ def layer_fwd_tc_(x, wcat, bias, bits, pb, rscales, y, stat_sums=None):
     return y
 
 
-def layer_adjT_tc_(x, bits, pb, rscales, col_scale):
-    """[32 nw, 128] = col_scale * (diag(rscale) A)^T x"""
+def layer_adjT_tc_(x, bits, pb, rscales, col_scale, with_colsum=False):
+    """[32 nw, 128] = col_scale * (diag(rscale) A)^T x;  with_colsum: 32 more rows, row 32 nw = column sums of x"""
     lib = _lib.load()
     m = x.shape[0]
-    out = torch.empty((32 * pb.nw, 128), dtype=torch.float32, device=x.device)
-    ws = workspace(lib.b2g_layer_adjT_tc_ws_bytes(pb.nw), x.device)
-    cost(4 * m * 128 + 4 * m * pb.nw + 4 * out.numel(), 2 * m * 128 * 32 * pb.nw)
+    nsub = pb.nw + (1 if with_colsum else 0)
+    out = torch.empty((32 * nsub, 128), dtype=torch.float32, device=x.device)
+    ws = workspace(lib.b2g_layer_adjT_tc_ws_bytes(nsub), x.device)
+    cost(4 * m * 128 + 4 * m * pb.nw + 4 * out.numel(), 2 * m * 128 * 32 * nsub)
     _run("b2g_layer_adjT_tc", lib.b2g_layer_adjT_tc, x.data_ptr(), bits.data_ptr(), ctypes.byref(pb.layout),
-         _ptr_array(list(rscales) + [None] * (4 - len(rscales))), _ptr(col_scale), m, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+         _ptr_array(list(rscales) + [None] * (4 - len(rscales))), _ptr(col_scale), m, int(bool(with_colsum)), out.data_ptr(), ws.data_ptr(),
+         ws.numel(), _stream())
     return out
 
 
@@ -895,21 +897,29 @@ class PatientSideFn(Function):
         if dout is not None:
             need_w = any(nig[3 + i] for i in range(n_w))
             need_b = any(has_bias[i] and nig[3 + n_w + i] for i in range(n_w))
-            if need_w or need_b:
-                dw = torch.empty((d, d), dtype=torch.float32, device=dev)
-                db = torch.empty(d, dtype=torch.float32, device=dev) if need_b else None
-                linear_bwd_weight_(dout, x_p, dw, db)
-                for i in range(n_w):
-                    if nig[3 + i]:
-                        dws[i] = dw
-                    if has_bias[i] and nig[3 + n_w + i]:
-                        dbs[i] = db
             want_y = [y_shapes[i] is not None and pb.in_rel[i] is not None and nig[3 + 2 * n_w + i] for i in range(nt)]
+            db = _tagged_colsum(dout) if need_b else None          # the producer of dout may have reduced its columns already
             if any(want_y) and pb.bits_in is not None:
-                dy_all = layer_adjT_tc_(dout, pb.bits_in, pb, pb.rscale_in(), None)
+                # dY_t = (diag(1/deg_t(p)) A_t)^T dout; the bias gradient (column sums of dout) rides along as one more column
+                fuse_b = need_b and db is None and pb.nw + 1 <= 16
+                dy_all = layer_adjT_tc_(dout, pb.bits_in, pb, pb.rscale_in(), None, with_colsum=fuse_b)
+                if fuse_b:
+                    db = dy_all[32 * pb.nw]
                 for i, (off, n) in enumerate(zip(pb.offs, pb.sizes)):
                     if want_y[i]:
                         dys[i] = dy_all[off:off + n]
+            if need_w or (need_b and db is None):
+                dw = torch.empty((d, d), dtype=torch.float32, device=dev)
+                db_new = torch.empty(d, dtype=torch.float32, device=dev) if (need_b and db is None) else None
+                linear_bwd_weight_(dout, x_p, dw, db_new)
+                db = db if db_new is None else db_new
+                for i in range(n_w):
+                    if nig[3 + i]:
+                        dws[i] = dw
+            if need_b:
+                for i in range(n_w):
+                    if has_bias[i] and nig[3 + n_w + i]:
+                        dbs[i] = db
         return (None, None, dx, *dws, *dbs, *dys)
 
 

@@ -149,6 +149,12 @@ def test_layer_adjT_tc(m, sizes, density, pkg):
         assert relmax(out[off:off + n], ref_t) < 2e-5
     out2 = ops.layer_adjT_tc_(x.to(dev), pb.bits_in, pb, rs, None)
     assert torch.equal(out, out2)
+    # column sums of x ride along as one more column of ones (the bias gradient when x = dout)
+    out3 = ops.layer_adjT_tc_(x.to(dev), pb.bits_in, pb, rs, None, with_colsum=True)
+    assert out3.shape == (32 * (pb.nw + 1), d)
+    assert relmax(out3[:32 * pb.nw], out) < 1e-6
+    assert relmax(out3[32 * pb.nw], xt.sum(0)) < 2e-5
+    assert float(out3[32 * pb.nw + 1:].abs().max()) == 0.0
 
 
 @pytest.mark.gpu
