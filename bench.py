@@ -1,8 +1,13 @@
 #!/usr/bin/env python
 """Benchmark of the hetero-GNN training hot path (BASELINE.json metric: train edges/sec, fwd+bwd, per
-HeteroConv step; workload: configs[1], the MIMIC-III-shaped synthetic graph "C2").
+HeteroConv step).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch_gpu] [--workload C4s8|C2|C3|C1]
+
+Default workload, at every N: "C4s8" = one GPU's share (1/8: 1.25 M patients, 12.5 M lab edges) of BASELINE.json
+configs[3], the patient-partitioned 10 M-patient / 100 M-edge graph the north_star's roofline and scaling targets are
+stated on; with --gpus 8 the eight shards ARE that graph (weak scaling: per-GPU work fixed).  configs[1] (the
+MIMIC-III-shaped graph "C2", 46,520 patients / 5 M lab edges, largely L2-resident) is `--workload C2`.
 
 One "step" = one full training step of the reference's Trainer.train_epoch (train.py:332-392) on the
 full graph: encode -> 2 x HeteroConv/BN/ReLU -> gated decoder over all train-split pairs -> weighted
@@ -12,8 +17,13 @@ HeteroConv layer application*: L * 2(E_l+E_d+E_m) per step (SURVEY.md section 8d
 value : device-timed (CUDA events), step inputs already resident in HBM.
 e2e   : the same step through the public Trainer API with HOST inputs: the step's pair indices, targets and
         supervision mask are copied from pinned host memory every step and the loss is read back.
-roofline : dominant libb2g kernel of one instrumented step (CUDA events around every library call).
-cpu_baseline : the oracle port (oracle/hetero_rgcn_ref.py, torch CPU, all host threads) on a bounded sample.
+roofline : ONE HeteroConv layer forward + backward against the layer's compulsory HBM traffic bytes_min (the
+           north_star's own yardstick); `roofline.dominant_kernel` keeps the per-launch numbers of the dominant libb2g kernel
+           of one instrumented step (CUDA events around every library call).
+cpu_baseline : the oracle port (oracle/hetero_rgcn_ref.py, torch CPU, all host threads): the full graph for C1 / C2
+           (BASELINE.md section 3), a bounded patient sample for the larger workloads.
+torch_eager_gpu : the same oracle port run eagerly on this B200 (PyTorch ATen kernels: index_select / index_add_ /
+           cuBLAS) -- the "PyTorch-eager on the same GPU" comparator of SURVEY.md 2.1; `--impl torch_gpu` prints it alone.
 """
 from __future__ import annotations
 
@@ -32,6 +42,10 @@ PKG = "multi-modal-gnn_b200"
 METRIC = "train_edges_per_sec_fwd_bwd_per_heteroconv_step"
 UNIT = "directed-edge-layer traversals/s"
 NUM_LAYERS = 2
+DEFAULT_WORKLOAD = "C4s8"
+# CPU oracle: full graph when it fits the box's memory / a few minutes, else 1/shrink of the patients (same density)
+CPU_SHRINK = {"tiny": 1, "C1": 1, "C2": 1, "C3": 16, "C4s8": 16, "C4": 128, "C5": 128}
+REF_MAX_STEPS = 5            # the CPU arm is bounded: at most this many timed oracle steps (a step takes seconds)
 
 
 def _cfg(dropout=0.2, loss="mse"):
@@ -57,45 +71,55 @@ def _peaks():
 # ------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port on a bounded sample of the workload
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_baseline_run(workload: str, steps: int, warmup: int, shrink: int = 16, loss: str = "mse"):
-    """Times oracle train steps (forward + weighted loss + backward + Adam, dropout 0.2 like the shipped config)
-    on a 1/shrink patient sample of the workload, with every host thread.  Returns (edges_per_s, ms, sample)."""
+def cpu_baseline_run(workload: str, steps: int, warmup: int, shrink: int = None, loss: str = "mse", device: str = "cpu"):
+    """Times oracle train steps (forward + weighted loss + backward + Adam, dropout 0.2 like the shipped config) on the
+    workload (or on a 1/shrink patient sample of it), with every host thread -- or, with device='cuda', eagerly on the GPU
+    (the PyTorch-eager comparator).  Returns (edges_per_s, ms, sample, cores)."""
     import torch
     pkg = importlib.import_module(PKG)
     from oracle import hetero_rgcn_ref as R
     spec = pkg.synth.SPECS[workload]
-    small = pkg.synth.GraphSpec(spec.name + f"/{shrink}", max(spec.n_patient // shrink, 64), spec.n_lab, spec.n_dx, spec.n_med,
-                                spec.e_lab // shrink, spec.e_dx // shrink, spec.e_med // shrink, spec.low_degree_frac)
+    if shrink is None:
+        shrink = CPU_SHRINK.get(workload, 16) if device == "cpu" else 1
+    small = spec if shrink == 1 else pkg.synth.GraphSpec(
+        spec.name + f"/{shrink}", max(spec.n_patient // shrink, 64), spec.n_lab, spec.n_dx, spec.n_med, spec.e_lab // shrink,
+        spec.e_dx // shrink, spec.e_med // shrink, spec.low_degree_frac)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    g = pkg.synth.make_graph(small, seed=42)
+    dev = torch.device(device)
+    big = small.n_patient >= 500_000
+    g = pkg.synth.make_graph(small, seed=42, device=("cuda" if (big and torch.cuda.is_available()) else "cpu")).to(dev)
     counts = {nt: int(g[nt].num_nodes) for nt in g.node_types}
     ets = list(g.edge_types)
-    sd = R.init_state(counts, ets, seed=0)
+    sd = {k: v.to(dev) for k, v in R.init_state(counts, ets, seed=0).items()}
     ei = g["patient", "has_lab", "lab"].edge_index
     attr = g["patient", "has_lab", "lab"].edge_attr
-    tr = R.split_masks(ei.shape[1])[0]
+    tr = R.split_masks(ei.shape[1])[0].to(dev)
     pi, li, tgt = ei[0][tr], ei[1][tr], attr[tr].squeeze(-1)
-    w = R.lab_weights(li, tgt, counts["lab"])
+    w = R.lab_weights(li.cpu(), tgt.cpu(), counts["lab"]).to(dev)
     keys = R.trainable_keys(sd)
     params = [sd[k].requires_grad_(True) for k in keys]
     opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-5)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        sup = R.supervision_mask(int(tr.sum()), 0.2, 1000 + it)
+        if device != "cpu":
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        sup = R.supervision_mask(int(tr.sum()), 0.2, 1000 + it).to(dev)
         opt.zero_grad()
         pred = R.predict_lab_values(sd, counts, ets, g.edge_index_dict, pi, li, True, p_drop=0.2)
         lossv = R.weighted_loss(pred, tgt, li, w, sup, loss)
         lossv.backward()
         opt.step()
-        float(lossv.detach())
+        float(lossv.detach())            # (a device -> host read: also the synchronisation point of the GPU variant)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     t = statistics.median(times)
     edges = NUM_LAYERS * small.directed_edges_per_layer
-    sample = (f"{workload} shrunk 1/{shrink}: {small.n_patient} patients, {small.e_lab}/{small.e_dx}/{small.e_med} edges, "
-              f"median of {steps} oracle train steps after {warmup} warm-up")
+    sample = ((f"{workload} (full graph): " if shrink == 1 else f"{workload} shrunk 1/{shrink}: ")
+              + f"{small.n_patient} patients, {small.e_lab}/{small.e_dx}/{small.e_med} edges, median of {steps} oracle train steps "
+              + f"after {warmup} warm-up" + ("" if device == "cpu" else ", PyTorch eager on the GPU"))
     return edges / t, t * 1e3, sample, cores
 
 
@@ -105,13 +129,39 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, ms, sample, cores = cpu_baseline_run(args.workload, args.steps, max(args.warmup, 1))
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    steps = max(1, min(args.steps, REF_MAX_STEPS))
+    v, ms, sample, cores = cpu_baseline_run(args.workload, steps, 1)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "sample": sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def run_torch_gpu(args):
+    """--impl torch_gpu: the oracle port run eagerly on the B200 (SURVEY.md 2.1 / 8d "secondary baseline": what PyTorch + PyG-style
+    index_select / index_add_ / cuBLAS would do for the same step on the same GPU).  Informative; not the reference arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    line = {"impl": "torch_gpu", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (ATen / cuBLAS eager)", "data": "synthetic",
+            "gpu_launches": 0}
+    line.update(torch_eager_gpu(args.workload, args.steps, max(args.warmup, 1)))
+    line["config"] = {"workload": args.workload, "sample": line.pop("sample", None)}
+    print(json.dumps(line), flush=True)
+
+
+def torch_eager_gpu(workload: str, steps: int, warmup: int):
+    import torch
+    try:
+        v, ms, sample, _ = cpu_baseline_run(workload, steps, warmup, shrink=1, device="cuda")
+        out = {"value": v, "ms_per_step": ms, "sample": sample, "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    except torch.OutOfMemoryError as exc:        # PyG-style message materialisation ([E, 128] fp32 per relation) does not fit
+        out = {"value": None, "ms_per_step": None, "unavailable": f"CUDA out of memory on the full {workload} graph: {str(exc)[:120]}"}
+    torch.cuda.empty_cache()
+    return out
 
 
 # C-ABI call -> the kernel that does its work.  Several entry points share one kernel (the tcgen05 linear kernel serves
@@ -125,18 +175,21 @@ KERNEL_OF = {
     "b2g_bn_bwd": "k_col_reduce<1>+k_bn_bwd_apply", "b2g_bn_bwd_sync": "k_col_reduce<1>+k_bn_bwd_apply",
     "b2g_linear_fwd": "k_sgemm_small", "b2g_linear_bwd_input": "k_sgemm_small", "b2g_linear_bwd_weight": "k_sgemm_small",
     "b2g_decoder_fwd_tc": "k_decoder_fwd_tc", "b2g_decoder_bwd_tc": "k_decoder_bwd_tc", "b2g_bn_apply": "k_bn_apply",
+    "b2g_layer_fwd_tc": "k_layer_tf32", "b2g_layer_adjT_tc": "k_adjT_tf32+k_adjT_reduce",
 }
 
 
 def _measured_traffic(kernel: str):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r1_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        with open(path) as f:
-            t = json.load(f)
-        return t.get(kernel)
-    except Exception:
-        return None
+    """DRAM bytes per launch of `kernel` from the committed ncu captures (profiles/r2_traffic.json, else r1_traffic.json), or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            if kernel in t:
+                return t[kernel]
+        except Exception:
+            pass
+    return None
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -259,7 +312,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # NCCL's own log (NCCL_DEBUG, if the caller sets it) goes wherever NCCL sends it: fd 1 is parked on stderr until the
+        # final JSON line, so stdout still carries exactly one line
         dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=90))
 
     spec = pkg.synth.SPECS[args.workload]
@@ -395,12 +449,13 @@ def run_ours(args):
         name, (ms, calls, nbytes, flops, members) = top[0], top[1]
         ach = nbytes / calls / (ms / calls * 1e-3) / 1e9          # algorithmic bytes per launch / average launch duration
         tr = _measured_traffic(name)
-        roof = {"bound": "hbm", "kernel": name, "entry_points": sorted(members), "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+        roof_kernel = {"bound": "hbm", "kernel": name, "entry_points": sorted(members), "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": ach / peaks["hbm"], "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
                 "algorithmic_bytes_per_launch": nbytes / calls, "launches_per_step": calls, "avg_launch_ms": ms / calls,
                 "share_of_step": a_share(ms, tot), "tensor_TFLOPs": flops / (ms * 1e-3) / 1e12,
                 "timing": "CUDA events around every library call of one eager step enqueued behind a 40 ms spin kernel (device time, no launch gaps), L2 flushed before the step",
                 "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if peaks["source"] == "measured" else "fallback"}
+        roof = dict(roof_kernel)                       # N > 1: the dominant kernel's numbers; N = 1: replaced by the layer roofline below
 
     if world > 1 and dctx.peer is not None:
         dctx.peer.check()                          # a timed-out rendezvous would have produced garbage: fail loudly
@@ -427,11 +482,48 @@ def run_ours(args):
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels, "final_loss": final_loss,
                 "step_ms_min_max": [min(step_ms), max(step_ms)]}
         if world == 1:
-            try:        # an extra, never a reason to lose the line
-                line["layer_microbench"] = layer_microbench(model, trainer, spec, dev, flush, _peaks()["hbm"])
+            # the north_star's yardstick: ONE HeteroConv layer forward + backward against its compulsory traffic
+            peaks = _peaks()
+            try:
+                mb = layer_microbench(model, trainer, spec, dev, flush, peaks["hbm"])
+                tr = _measured_traffic("hetero_layer_fwd_bwd:" + args.workload)
+                line["roofline"] = {"bound": "hbm", "kernel": "one HeteroConv layer, forward + backward (k_layer_tf32 x2, k_adjT_tf32 x2, "
+                                    "k_wgrad_tf32, grouped type-row GEMMs)", "achieved": mb["achieved_GBps_of_bytes_min"],
+                                    "peak": peaks["hbm"], "unit": "GB/s", "frac": mb["frac_of_hbm_peak"],
+                                    "traffic": (tr or {}).get("dram_bytes_per_layer"), "traffic_source": (tr or {}).get("source"),
+                                    "algorithmic_bytes": mb["bytes_min"], "ms": mb["ms"], "directed_edges_per_s": mb["directed_edges_per_s"],
+                                    "what": mb["what"] + "; algorithmic bytes = bytes_min = 5 N_p d 4 + 2 E 4 + 6 (N_p + 1) 4 (SURVEY.md 8d)",
+                                    "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if peaks["source"] == "measured" else "fallback",
+                                    "dominant_kernel": roof}
+            except Exception as exc:      # noqa: BLE001   (an extra must never lose the line)
+                line["roofline"] = dict(roof or {}, layer_error=f"{type(exc).__name__}: {exc}")
+            # the parity-claim mode (exact fp32 kernels: aggregation <= 1e-5) timed on the same workload, eagerly
+            try:
+                trainer.enable_cuda_graph(False)
+                ops.set_precision("fp32")
+                step_device(0)
+                torch.cuda.synchronize()
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record()
+                for i in range(2):
+                    step_device(i)
+                e_.record()
+                torch.cuda.synchronize()
+                ms32 = s_.elapsed_time(e_) / 2
+                line["exact_fp32_mode"] = {"ms_per_step": ms32, "value": edges_per_step / (ms32 * 1e-3), "unit": UNIT, "steps": 2,
+                                           "what": "the same step with every product in exact fp32 (SIMT kernels, CSR gather-reduce): the mode the 1e-5 "
+                                                   "aggregation / golden-vector parity claims are made in; eager launches"}
             except Exception as exc:      # noqa: BLE001
-                line["layer_microbench"] = {"error": f"{type(exc).__name__}: {exc}"}
+                line["exact_fp32_mode"] = {"error": f"{type(exc).__name__}: {exc}"}
+            finally:
+                ops.set_precision("tf32")
         if world == 1 and not args.no_cpu_baseline:
+            # free the GPU arm's memory before the comparators run
+            del trainer, model
+            torch.cuda.empty_cache()
+            te = torch_eager_gpu(args.workload, 2, 1)
+            te["unit"] = UNIT
+            line["torch_eager_gpu"] = te
             v, ms, sample, cores = cpu_baseline_run(args.workload, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
         sys.stdout.flush()
@@ -450,13 +542,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step launch by launch instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     else:
         if args.warmup < 3:
             args.warmup = 3

@@ -278,7 +278,9 @@ size_t b2g_comm_max_bytes(void);      /* largest payload of one b2g_comm_allredu
 int b2g_comm_local_alloc(void** region, unsigned char* h_handle64);
 int b2g_comm_create(int rank, int world, void* local_region, const unsigned char* h_handles, b2g_comm_t** out);
 int b2g_comm_destroy(b2g_comm_t* comm);
-int b2g_comm_error(b2g_comm_t* comm);  /* SYNC: 1 if a wait timed out (a rank did not show up within ~30 s) */
+int b2g_comm_error(b2g_comm_t* comm);  /* SYNC: 1 if a wait timed out (a rank did not show up within the time-out) */
+/* seconds a rendezvous waits for a peer before giving up (default ~30 s; also B2G_PEER_TIMEOUT_S at creation) */
+int b2g_comm_set_timeout(b2g_comm_t* comm, double seconds);
 /* out[i] = sum over ranks of in[i] (in == out allowed), one-shot: every rank stores its payload in its own
  * region, signals every peer, and adds everybody's payload in RANK ORDER (bit-identical on all ranks,
  * deterministic).  Payload: a multiple of 16 bytes, 16-byte aligned, <= b2g_comm_max_bytes().  Every rank

@@ -136,6 +136,7 @@ _PROTOS = {
     "b2g_comm_create": (c_int, [c_int, c_int, _P, ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
     "b2g_comm_destroy": (c_int, [_P]),
     "b2g_comm_error": (c_int, [_P]),
+    "b2g_comm_set_timeout": (c_int, [_P, ctypes.c_double]),
     "b2g_comm_allreduce_f32": (c_int, [_P, _P, _P, c_int64, _P]),
     "b2g_comm_allreduce_f64": (c_int, [_P, _P, _P, c_int64, _P]),
     "b2g_bn_stats_sync": (c_int, [_P, _P, c_int64, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),

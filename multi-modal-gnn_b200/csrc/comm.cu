@@ -1,6 +1,7 @@
 // Peer-memory communicator: CUDA-IPC setup of the symmetric regions and the one-shot all-reduce kernels (peer.cuh).
 // Replaces the NCCL launches of the latency-bound exchanges of the patient-partitioned mode; NCCL (torch.distributed)
 // stays the plumbing for setup-time integer all-reduces and anything larger than the slices hold.
+#include <stdlib.h>
 #include <string.h>
 #include "peer.cuh"
 
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(AR_THREADS) k_peer_allreduce(PeerCtx c, const 
 }
 }  // namespace
 
+extern "C" int b2g_comm_set_timeout(b2g_comm* c, double seconds);
 extern "C" size_t b2g_comm_region_bytes(void) { return b2g::PEER_REGION_BYTES; }
 extern "C" size_t b2g_comm_max_bytes(void) { return (size_t)b2g::PEER_AR_SLOTS * b2g::PEER_SLICE_BYTES; }
 
@@ -101,7 +103,19 @@ extern "C" int b2g_comm_create(int rank, int world, void* local_region, const un
   c->error = (int*)(c->seq + b2g::PEER_SLOTS);
   c->ctx.seq = c->seq;
   c->ctx.error = c->error;
+  c->ctx.max_spins = 1 << 25;
+  if (const char* e = getenv("B2G_PEER_TIMEOUT_S")) b2g_comm_set_timeout(c, atof(e));
   *out = c;
+  return B2G_OK;
+}
+
+/* Seconds a rendezvous may wait for a peer before it gives up and raises the error flag (default ~30). */
+extern "C" int b2g_comm_set_timeout(b2g_comm* c, double seconds) {
+  B2G_CHECK_ARG(c && seconds > 0, "comm_set_timeout: bad args");
+  double spins = seconds * ((double)(1 << 25) / 30.0);
+  if (spins < 8192) spins = 8192;
+  if (spins > 2.0e9) spins = 2.0e9;
+  c->ctx.max_spins = (int)spins;
   return B2G_OK;
 }
 

@@ -14,9 +14,11 @@
 // Sequence numbers live in device memory and are advanced by the kernel itself, so a captured CUDA graph can be
 // replayed.  Two parities make the scheme safe without a second barrier: nobody can reach call n+2 on a slot (and
 // overwrite the parity of call n) before everybody has signalled call n+1, i.e. finished reading call n.
-// A spin that does not complete within ~30 s (ranks can be skewed by seconds while they build their graph indices or load
-// modules) sets the error flag and gives up instead of hanging the GPU; once the flag is set every later wait returns at
-// once, so a dead peer costs one timeout, not one per exchange.
+// A spin that does not complete within the time-out (default ~30 s: ranks can be skewed by seconds while they build their graph
+// indices or load modules; b2g_comm_set_timeout / B2G_PEER_TIMEOUT_S) sets the error flag and gives up instead of hanging the
+// GPU; once the flag is set every later wait returns at once, so a dead peer costs one time-out, not one per exchange.  Results
+// after a time-out are garbage: the host checks the flag at its next synchronisation point (Trainer.train_epoch / validate,
+// bench.py) and raises.
 #pragma once
 #include "common.cuh"
 
@@ -36,6 +38,7 @@ struct PeerCtx {
   uint8_t* base[PEER_MAX_WORLD];   // base[r]: rank r's symmetric region as mapped in THIS process (base[rank] = own)
   uint32_t* seq;                   // [PEER_SLOTS], local
   int* error;                      // local; set when a wait timed out
+  int max_spins;                   // polls before a wait gives up (2^25 ~ 30 s; b2g_comm_set_timeout / B2G_PEER_TIMEOUT_S)
 };
 
 #ifdef __CUDACC__
@@ -83,7 +86,7 @@ __device__ __forceinline__ void peer_signal_wait(const PeerCtx& c, int slot, uin
     const uint32_t* f = reinterpret_cast<const uint32_t*>(c.base[c.rank]) + (size_t)slot * PEER_MAX_WORLD + r;
     bool ok = false;
     const bool dead = *reinterpret_cast<volatile int*>(c.error) != 0;      // an earlier wait already timed out
-    for (int it = 0; it < (dead ? 1 : (1 << 25)); ++it) {
+    for (int it = 0; it < (dead ? 1 : c.max_spins); ++it) {
       if ((int32_t)(ld_volatile_u32(f) - seq) >= 0) {
         ok = true;
         break;

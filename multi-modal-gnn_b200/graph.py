@@ -28,14 +28,21 @@ def _stream():
 
 
 _WS: Dict[int, torch.Tensor] = {}
+_WS_RETIRED: Dict[int, list] = {}
 
 
 def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    """Grow-only scratch buffer per device (all library calls are stream-ordered on the current stream)."""
+    """Grow-only scratch buffer per device (all library calls are stream-ordered on the current stream).  A buffer that is
+    outgrown is RETIRED, not freed: a captured CUDA graph may have its address baked in (Trainer._capture), and replaying it
+    after the allocator handed that memory to another tensor would corrupt it.  Growth is geometric, so the retired buffers
+    sum to less than the live one."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
     buf = _WS.get(idx)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=torch.device("cuda", idx))
+        size = max(int(nbytes), 1 << 20, 2 * buf.numel() if buf is not None else 0)
+        if buf is not None:
+            _WS_RETIRED.setdefault(idx, []).append(buf)
+        buf = torch.empty(size, dtype=torch.uint8, device=torch.device("cuda", idx))
         _WS[idx] = buf
     return buf
 
@@ -150,6 +157,13 @@ class DenseAdjacency:
 
     def __init__(self, mat, pad, n_small, n_big, big_is_dst):
         self.mat, self.pad, self.n_small, self.n_big, self.big_is_dst = mat, pad, n_small, n_big, big_is_dst
+        self._nbytes = int(mat.numel()) * 4
+
+    def __del__(self):                       # give the budget back when the relation (graph) dies
+        try:
+            DenseAdjacency.bytes_in_use -= self._nbytes
+        except Exception:
+            pass
 
 
 def bit_layout(sizes):

@@ -201,8 +201,10 @@ class HeteroRGCN(nn.Module):
         self._seed_buffer: Optional[torch.Tensor] = None      # set by Trainer.enable_cuda_graph()
         self._embedding_cache_on = False                      # enable_embedding_cache(): eval-mode (init, x) reuse
         self._embedding_cache = None
+        self._generation = 0
         self.dist: Optional[DistContext] = None               # set by set_distributed(): patient-partitioned multi-GPU
         self._register_load_state_dict_pre_hook(self._rename_pyg24_keys)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.bump_generation())
         logging.info(f"Initialized HeteroRGCN with hidden_dim={hidden_dim}, num_layers={num_layers}")
 
     # ------------------------------------------------------------------------------------------
@@ -291,7 +293,13 @@ class HeteroRGCN(nn.Module):
                         local_ys.append((ys, len(ys)))
                     ys.append(None)
                 else:                              # many sources: aggregate first, then transform
-                    agg = ops.MeanAggFn.apply(x[et[0]], rel)
+                    x_src = x[et[0]]
+                    if src_replicated and rep is None:
+                        # a replicated table consumed by this rank's rows only: every rank holds a PARTIAL gradient of it, which
+                        # must be summed over ranks before it meets the 1/world of rep_param (the few-source branch does the same
+                        # through `local_ys`)
+                        x_src = replicated_to_local(x_src, dctx)
+                    agg = ops.MeanAggFn.apply(x_src, rel)
                     if partial_sources:            # partial mean over this rank's sources -> sum over ranks
                         partial_aggs.append((aggs, len(aggs)))
                     aggs.append(agg)
@@ -354,7 +362,8 @@ class HeteroRGCN(nn.Module):
         ys_live = replicated_to_local_many(ys_live, dctx)  # consumed by rank-local rows: gradients are summed over ranks
         it = iter(ys_live)
         ys = [None if rel is None else next(it) for rel in pb.in_rel]
-        res = ops.PatientSideFn.apply(pb, len(w_roots), x[hub], *w_roots, *b_roots, *ys)
+        want_stats = self.training and self.use_batch_norm          # BatchNorm follows (model.py:259-261): statistics in the epilogue
+        res = ops.PatientSideFn.apply(pb, len(w_roots), want_stats, x[hub], *w_roots, *b_roots, *ys)
         out = {hub: res[0]}
         out_types = [i for i, rel in enumerate(pb.out_rel) if rel is not None and pb.types[i] in by_dst]
         aggs = partial_to_replicated_many([res[1 + i] for i in out_types], dctx)     # partial neighbour sums -> all ranks
@@ -406,7 +415,18 @@ class HeteroRGCN(nn.Module):
         self._embedding_cache = None
 
     def _state_versions(self):
-        return tuple(t._version for t in self.parameters()) + tuple(t._version for t in self.buffers())
+        """Cache key: an explicit generation counter (bumped by train(), load_state_dict() and by this package's Trainer /
+        FusedAdam after every optimizer step -- they write parameters through raw pointers, also inside replayed CUDA graphs,
+        where tensor version counters do not move) plus the tensors' own version counters (torch.optim, manual edits)."""
+        return (self._generation,) + tuple(t._version for t in self.parameters()) + tuple(t._version for t in self.buffers())
+
+    def bump_generation(self):
+        self._generation += 1
+        self._embedding_cache = None
+
+    def train(self, mode: bool = True):
+        self.bump_generation()
+        return super().train(mode)
 
     def _eval_embeddings(self, data, gi: GraphIndex, node_types, streams):
         """(init, x) for eval mode: model.py:294 and :301 (one encode serves both, as dropout is off)."""
@@ -458,6 +478,8 @@ class HeteroRGCN(nn.Module):
             return torch.cat(out_p), torch.cat(out_l), torch.cat(out_v)
         finally:
             self._embedding_cache_on = was_on
+            if not was_on:
+                self._embedding_cache = None          # the cache was forced on for this call only
 
     def _check_device(self):
         if self._device().type != "cuda":
@@ -575,6 +597,9 @@ class _PairPlan:
         self.low_mask = torch.zeros(self.m, dtype=torch.uint8, device=pi.device)
         if self.m == 0:
             return
+        lo = torch.stack([pi64.min(), li64.min(), pi64.max(), li64.max()]).tolist()      # one host sync (another follows below)
+        if lo[0] < 0 or lo[1] < 0 or lo[2] >= n_p or lo[3] >= n_l:
+            raise IndexError(f"patient / lab indices out of range: patients in [{lo[0]}, {lo[2]}] of {n_p}, labs in [{lo[1]}, {lo[3]}] of {n_l}")
         if gi.patient_lab_degree is None:
             raise _lib.B2GError("graph has no ('patient','has_lab','lab') relation: cannot compute the degree gate")
         _lib.check(lib.b2g_degree_gate(gi.patient_lab_degree.data_ptr(), pi64.data_ptr(), self.m, int(threshold),

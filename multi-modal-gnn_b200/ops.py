@@ -91,6 +91,19 @@ def _tagged_colsum(t: torch.Tensor):
     return tag[0]
 
 
+# BatchNorm column statistics {sum x, sum x^2} (fp64 [2 d]) that the PRODUCER of a tensor computed in its epilogue
+# (csrc/layer_tc.cu): the BatchNorm that follows skips its own pass over the rows.  Same validity rule as above.
+def _tag_bnsums(t: torch.Tensor, sums: torch.Tensor):
+    t._b2g_bnsums = (sums, t._version, t.data_ptr())
+
+
+def _tagged_bnsums(t: torch.Tensor):
+    tag = getattr(t, "_b2g_bnsums", None)
+    if tag is None or tag[1] != t._version or tag[2] != t.data_ptr():
+        return None
+    return tag[0]
+
+
 # --------------------------------------------------------------------------------------------------
 # raw (non-differentiable) kernel calls
 # --------------------------------------------------------------------------------------------------
@@ -453,7 +466,11 @@ class BNActDropFn(Function):
         dev = x.device
         mean = torch.empty(d, dtype=torch.float32, device=dev)
         rstd = torch.empty(d, dtype=torch.float32, device=dev)
-        if training:
+        sums = _tagged_bnsums(x) if training else None
+        if training and sums is not None:        # the producing kernel's epilogue already reduced the columns
+            _run("b2g_bn_finalize_sums", lib.b2g_bn_finalize_sums, sums.data_ptr(), m, d, float(eps), float(momentum), mean.data_ptr(),
+                 rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), _stream())
+        elif training:
             ws = workspace(lib.b2g_bn_ws_bytes(d), dev)
             cost(4 * m * d)
             _run("b2g_bn_stats", lib.b2g_bn_stats, x.data_ptr(), m, d, float(eps), float(momentum), mean.data_ptr(), rstd.data_ptr(),
@@ -507,7 +524,13 @@ class SyncBNActDropFn(Function):
         rstd = torch.empty(d, dtype=torch.float32, device=dev)
         peer = getattr(dctx, "peer", None)
         cost(4 * m * d)
-        if peer is not None:      # statistics + NVLink exchange + finalisation in ONE kernel (csrc/peer.cuh)
+        tagged = _tagged_bnsums(x)
+        if tagged is not None:    # local totals came out of the producing kernel's epilogue: exchange 2 KB, finalise
+            sums = tagged.clone()
+            dctx.all_reduce_(sums)
+            _run("b2g_bn_finalize_sums", lib.b2g_bn_finalize_sums, sums.data_ptr(), int(m_total), d, float(eps), float(momentum),
+                 mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), _stream())
+        elif peer is not None:      # statistics + NVLink exchange + finalisation in ONE kernel (csrc/peer.cuh)
             _run("b2g_bn_stats_sync", lib.b2g_bn_stats_sync, peer.handle, x.data_ptr(), m, int(m_total), d, float(eps), float(momentum),
                  mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), ws.data_ptr(), ws.numel(), _stream())
             dctx.count_fused()
@@ -835,7 +858,7 @@ class PatientSideFn(Function):
     outputs: out_p, agg_t for t in pb.types (a zero-row tensor when there is no relation patient -> t)."""
 
     @staticmethod
-    def forward(ctx, pb, n_w, x_p, *tensors):
+    def forward(ctx, pb, n_w, want_stats, x_p, *tensors):
         nt = len(pb.types)
         w_roots = [_f32(t, "W_root") for t in tensors[:n_w]]
         biases = [None if t is None else _f32(t, "b_root") for t in tensors[n_w:2 * n_w]]
@@ -847,7 +870,10 @@ class PatientSideFn(Function):
         wcat, bias = layer_cat_weights_(w_roots, False, ys_in, [None] * nt, pb.offs, d, ktot, d, biases)
         out = torch.empty((m, d), dtype=torch.float32, device=x_p.device)
         if pb.bits_in is not None and any(y is not None for y in ys_in):
-            layer_fwd_tc_(x_p, wcat, bias, pb.bits_in, pb, pb.rscale_in(), out)
+            sums = torch.empty(2 * d, dtype=torch.float64, device=x_p.device) if (want_stats and d <= 128) else None
+            layer_fwd_tc_(x_p, wcat, bias, pb.bits_in, pb, pb.rscale_in(), out, sums)
+            if sums is not None:
+                _tag_bnsums(out, sums)          # BatchNorm statistics of the layer output (model.py:259-261) for free
         else:
             linear_fwd_(x_p, wcat[:, :d].contiguous(), bias, out)
         aggs = []
@@ -869,7 +895,7 @@ class PatientSideFn(Function):
         x_p, w_roots = saved[0], list(saved[1:1 + n_w])
         nt = len(pb.types)
         m, d = x_p.shape
-        nig = ctx.needs_input_grad            # (pb, n_w, x_p, W.., b.., Y..)
+        nig = ctx.needs_input_grad[1:]        # (n_w, want_stats | x_p, W.., b.., Y..) -> indices below count from n_w = 0
         dev = x_p.device
         dx = None
         dws = [None] * n_w
@@ -920,7 +946,7 @@ class PatientSideFn(Function):
                 for i in range(n_w):
                     if has_bias[i] and nig[3 + n_w + i]:
                         dbs[i] = db
-        return (None, None, dx, *dws, *dbs, *dys)
+        return (None, None, None, dx, *dws, *dbs, *dys)
 
 
 class PairAddReluFn(Function):

@@ -87,6 +87,9 @@ class FusedAdam(torch.optim.Optimizer):
                 _lib.check(lib.b2g_adam_step(d_desc.data_ptr(), len(ps), d_chunks.data_ptr(), n_chunks, group["lr"] / bc1, bc2 ** 0.5,
                                              1.0 - beta1, beta2, 1.0 - beta2, group["eps"], group["weight_decay"],
                                              torch.cuda.current_stream().cuda_stream), "b2g_adam_step")
+                # the kernel wrote through raw pointers: move the tensors' version counters like an in-place op would (caches keyed
+                # on parameter versions, e.g. HeteroRGCN's eval-mode embedding cache, must see the update)
+                torch.autograd.graph.increment_version(ps)
                 self.launches += 1
         return loss
 

@@ -177,6 +177,8 @@ class Trainer:
         static device buffers before every replay; the optimizer step stays eager."""
         self._use_graph = bool(enabled)
         self._graph = None
+        if not enabled:
+            self.model._seed_buffer = None        # eager steps draw a fresh host seed per call again
 
     def _loss_of(self, pred, edge_values, lab_indices, sup):
         if self.loss_fn in ("mae", "mse"):
@@ -247,6 +249,7 @@ class Trainer:
         self.model._seed_buffer.fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
         g["graph"].replay()
         self.optimizer.step()
+        self.model.bump_generation()              # the replay wrote parameters / buffers through raw pointers
         return g["loss"]
 
     def train_step(self, patient_indices, lab_indices, edge_values, supervision_mask) -> torch.Tensor:
@@ -260,7 +263,14 @@ class Trainer:
         if self.grad_hook is not None:
             self.grad_hook()
         self.optimizer.step()
+        self.model.bump_generation()
         return loss
+
+    def _check_exchange(self):
+        """After a host synchronisation: a timed-out peer rendezvous (csrc/peer.cuh) means every exchange since summed garbage --
+        stop instead of training on."""
+        if self.dist is not None and getattr(self.dist, "peer", None) is not None:
+            self.dist.peer.check()
 
     def train_epoch(self, seed: Optional[int] = None) -> float:
         """train.py:332-392."""
@@ -268,7 +278,9 @@ class Trainer:
         _, ev, _, sup = self.masker.get_masked_data("train", seed)
         pi, li = self.masker.split_rows("train")
         sup_dev = sup.to(self.device, non_blocking=True)
-        return float(self.train_step(pi, li, ev, sup_dev).item())
+        loss = float(self.train_step(pi, li, ev, sup_dev).item())
+        self._check_exchange()
+        return loss
 
     @torch.no_grad()
     def validate(self, split: str = "val") -> float:
@@ -277,4 +289,6 @@ class Trainer:
         _, ev, _, _ = self.masker.get_masked_data(split)
         pi, li = self.masker.split_rows(split)
         pred = self.model.predict_lab_values(self.data, pi, li)
-        return float(compute_regression_loss(pred, ev, loss_type=self.loss_fn).item())
+        out = float(compute_regression_loss(pred, ev, loss_type=self.loss_fn).item())
+        self._check_exchange()
+        return out

@@ -216,3 +216,41 @@ def test_fused_layer_equals_per_relation_path(spec_name, n_p, pkg):
         e_f, e_u = relmax(fused[k], exact[k]), relmax(unfused[k], exact[k])
         assert e_f < 5e-3, f"{k}: fused tf32 vs exact fp32 {e_f:.2e}"
         assert e_u < 5e-3, f"{k}: per-relation tf32 vs exact fp32 {e_u:.2e}"
+
+
+@pytest.mark.gpu
+def test_batchnorm_statistics_come_from_the_layer_epilogue(pkg):
+    """The patient BatchNorm after a fused layer (model.py:259-261) takes {sum x, sum x^2} from k_layer_tf32's epilogue
+    (b2g_bn_finalize_sums) instead of a pass of its own; outputs and running buffers equal the separate-pass result."""
+    G, ops, M, S, L = _mods()
+    dev = torch.device("cuda:0")
+    g = S.make_graph(S.GraphSpec("t", 3000, 50, 114, 100, 90000, 8000, 24000, 0.05), seed=2).to(dev)
+    cfg = {"model": {"architecture": "RGCN", "hidden_dim": 128, "num_layers": 2, "dropout": 0.0, "use_batch_norm": True, "activation": "relu"}}
+    old = ops.PRECISION
+    ops.set_precision("tf32")
+    try:
+        res = {}
+        for fused in (True, False):
+            torch.manual_seed(0)
+            model = M.build_model(cfg, (g.node_types, g.edge_types), None).to(dev)
+            model._init_embeddings(g)
+            model.train()
+            saved = M.HeteroRGCN._layer_fused
+            if not fused:
+                M.HeteroRGCN._layer_fused = lambda self, *a, **k: None
+            try:
+                ops.PROFILE = []
+                out = model(g)
+                names = [p[0] for p in ops.PROFILE]
+            finally:
+                ops.PROFILE = None
+                M.HeteroRGCN._layer_fused = saved
+            res[fused] = (out, {k: v.clone() for k, v in model.state_dict().items() if "running" in k}, names)
+        assert res[True][2].count("b2g_bn_finalize_sums") == 2, "both GNN layers' patient BatchNorms should use the epilogue statistics"
+        assert res[True][2].count("b2g_bn_stats") == res[False][2].count("b2g_bn_stats") - 2
+        for nt in res[True][0]:
+            assert relmax(res[True][0][nt], res[False][0][nt]) < 5e-3, nt
+        for k in res[True][1]:
+            assert relmax(res[True][1][k], res[False][1][k]) < 2e-3, k
+    finally:
+        ops.set_precision(old)

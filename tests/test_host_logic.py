@@ -138,4 +138,4 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "train_edges_per_sec_fwd_bwd_per_heteroconv_step" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"] == "C2" and "sample" in d["config"]
+    assert d["config"]["workload"] == "C4s8" and "sample" in d["config"]
