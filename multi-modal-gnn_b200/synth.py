@@ -53,6 +53,9 @@ class GraphSpec:
 # BASELINE.json configs (sizes from SURVEY.md section 8d).
 SPECS = {
     "tiny": GraphSpec("tiny", 300, 20, 30, 25, 4200, 700, 1500, low_degree_frac=0.15),
+    # more diagnosis / medication nodes than a rank's patient share (multi-GPU corner case: a replicated table that is larger
+    # than the rank-local destination set; tools/dist_check.py)
+    "wide": GraphSpec("wide", 160, 20, 114, 100, 1600, 480, 1400, low_degree_frac=0.1),
     "C1": GraphSpec("C1", 1834, 50, 114, 100, 61484, 5421, 15933, low_degree_frac=0.01),
     "C2": GraphSpec("C2", 46520, 160, 200, 100, 5_000_000, 441_000, 1_296_000, low_degree_frac=0.01),
     "C3": GraphSpec("C3", 1_000_000, 50, 200, 100, 20_000_000, 1_764_000, 5_182_000, low_degree_frac=0.12),

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--workload", default="C4s8")
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only-layer", action="store_true", help="skip the per-kernel timings (for ncu captures of one layer)")
     args = ap.parse_args()
     import torch
     pkg = importlib.import_module(PKG)
@@ -65,7 +66,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gen = torch.Generator(device=dev).manual_seed(7)
     res = {"workload": args.workload, "n_patient": m, "nw": pb.nw if pb else None, "hbm_peak_gbs": peaks}
-    if pb is not None:
+    if pb is not None and not args.only_layer:
         x = torch.randn(m, d, device=dev, generator=gen)
         ys = [torch.randn(n, d, device=dev, generator=gen) for n in pb.sizes]
         w = torch.randn(d, d, device=dev, generator=gen) / d ** 0.5
@@ -98,7 +99,7 @@ def main():
     e_und = spec.e_lab + spec.e_dx + spec.e_med
     bytes_min = 5 * m * d * 4 + 2 * e_und * 4 + 6 * (m + 1) * 4
     saved = M.HeteroRGCN._layer_fused
-    for label, fn in [("layer_fused", saved), ("layer_per_relation", lambda self, *a, **k: None)]:
+    for label, fn in [("layer_fused", saved)] + ([] if args.only_layer else [("layer_per_relation", lambda self, *a, **k: None)]):
         M.HeteroRGCN._layer_fused = fn
         try:
             med, mn = timed(once, args.reps, flush)
