@@ -325,6 +325,12 @@ int b2g_adam_step(const b2g_adam_tensor_t* d_tensors, int n_tensors, const int32
 int b2g_eval_fields(void);
 int b2g_eval_per_lab(const float* pred, const float* target, const int32_t* rowptr, const int32_t* pair_of, int n_lab,
                      int winsorize, float n_sigma, double* out, float* pred_w, void* stream);
+/* b2g_eval_per_lab + the patient-degree strata of evaluate.py:237-287: out_bins[n_lab][3][7] (double) per lab and degree
+ * group {1-5, 6-15, 16+ observed labs}: n, sum |r|, sum r^2, sum t, sum t^2, sum |r/t| (t != 0), count(t != 0) on the
+ * winsorised residuals; patient_idx int64[M], degree int64[N_patient] (bincount of has_lab sources). */
+int b2g_eval_per_lab_strata(const float* pred, const float* target, const int32_t* rowptr, const int32_t* pair_of,
+                            const int64_t* patient_idx, const int64_t* degree, int n_lab, int winsorize, float n_sigma,
+                            double* out, double* out_bins, float* pred_w, void* stream);
 
 /* y = dropout(relu(x)) without normalisation (EdgeRegressionHead, model.py:377-380) and its backward
  * (dx = dy * mask * [y > 0]); in-place allowed. */

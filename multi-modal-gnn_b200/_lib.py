@@ -147,6 +147,7 @@ _PROTOS = {
                               ctypes.c_double, ctypes.c_double, _P]),
     "b2g_eval_fields": (c_int, []),
     "b2g_eval_per_lab": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, _P, _P, _P]),
+    "b2g_eval_per_lab_strata": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P, _P, _P, _P]),
     "b2g_small_gemm_group": (c_int, [ctypes.POINTER(GemmProblemT), c_int, _P]),
     "b2g_small_colsum_group": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                        c_int, _P]),

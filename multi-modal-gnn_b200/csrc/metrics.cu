@@ -22,10 +22,14 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {   // all thr
   return t;
 }
 
+constexpr int EV_BINS = 3;      // patient-degree strata of evaluate.py:268-272: 1-5, 6-15, 16+ observed labs
+constexpr int EV_BIN_FIELDS = 7;   // n, sum|r|, sum r^2, sum t, sum t^2, sum |r/t| (t != 0), n(t != 0)
+
 __global__ void __launch_bounds__(EV_THREADS) k_eval_per_lab(const float* __restrict__ pred, const float* __restrict__ target,
                                                              const int32_t* __restrict__ rowptr, const int32_t* __restrict__ pair_of,
                                                              int winsorize, float n_sigma, double* __restrict__ out,
-                                                             float* __restrict__ pred_w) {
+                                                             float* __restrict__ pred_w, const int64_t* __restrict__ patient_idx,
+                                                             const int64_t* __restrict__ degree, double* __restrict__ out_bins) {
   __shared__ double sh[EV_THREADS / 32];
   const int lab = blockIdx.x;
   const int b = rowptr[lab], e = rowptr[lab + 1];
@@ -46,6 +50,11 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_per_lab(const float* __rest
   const bool clip = winsorize && n > 1;                      // evaluate.py:424 `if len(lab_residuals) > 1`
   const float lo = (float)(mean - (double)n_sigma * sd), hi = (float)(mean + (double)n_sigma * sd);
   double a_abs = 0, a_sq = 0, a_t = 0, a_t2 = 0, a_ape = 0, a_nz = 0, a_cap = 0;
+  double bins[EV_BINS][EV_BIN_FIELDS];
+#pragma unroll
+  for (int g = 0; g < EV_BINS; ++g)
+#pragma unroll
+    for (int f = 0; f < EV_BIN_FIELDS; ++f) bins[g][f] = 0.0;
   for (int j = b + threadIdx.x; j < e; j += EV_THREADS) {
     const int p = pair_of[j];
     const float t = target[p];
@@ -66,6 +75,26 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_per_lab(const float* __rest
       a_ape += fabs(d / (double)t);
       a_nz += 1.0;
     }
+    if (out_bins) {                                          // evaluate.py:237-287: strata of the pair's patient degree
+      const int64_t dg = degree[patient_idx[p]];
+      const int g = dg >= 16 ? 2 : (dg >= 6 ? 1 : (dg >= 1 ? 0 : -1));
+#pragma unroll
+      for (int q = 0; q < EV_BINS; ++q) {
+        const double on = (q == g) ? 1.0 : 0.0;
+        bins[q][0] += on; bins[q][1] += on * fabs(d); bins[q][2] += on * d * d; bins[q][3] += on * (double)t;
+        bins[q][4] += on * (double)t * (double)t;
+        if (t != 0.f) { bins[q][5] += on * fabs(d / (double)t); bins[q][6] += on; }
+      }
+    }
+  }
+  if (out_bins) {
+#pragma unroll
+    for (int g = 0; g < EV_BINS; ++g)
+#pragma unroll
+      for (int f = 0; f < EV_BIN_FIELDS; ++f) {
+        const double v = block_sum(bins[g][f], sh);
+        if (threadIdx.x == 0) out_bins[((size_t)lab * EV_BINS + g) * EV_BIN_FIELDS + f] = v;
+      }
   }
   a_abs = block_sum(a_abs, sh); a_sq = block_sum(a_sq, sh); a_t = block_sum(a_t, sh); a_t2 = block_sum(a_t2, sh);
   a_ape = block_sum(a_ape, sh); a_nz = block_sum(a_nz, sh); a_cap = block_sum(a_cap, sh);
@@ -86,7 +115,25 @@ extern "C" int b2g_eval_per_lab(const float* pred, const float* target, const in
                                 int winsorize, float n_sigma, double* out, float* pred_w, void* stream_) {
   B2G_CHECK_ARG(n_lab >= 0 && (n_lab == 0 || (pred && target && rowptr && pair_of && out)) && n_sigma >= 0.f, "eval_per_lab: bad args");
   if (n_lab == 0) return B2G_OK;
-  k_eval_per_lab<<<(unsigned)n_lab, EV_THREADS, 0, (cudaStream_t)stream_>>>(pred, target, rowptr, pair_of, winsorize, n_sigma, out, pred_w);
+  k_eval_per_lab<<<(unsigned)n_lab, EV_THREADS, 0, (cudaStream_t)stream_>>>(pred, target, rowptr, pair_of, winsorize, n_sigma, out, pred_w,
+                                                                            nullptr, nullptr, nullptr);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+/* The same pass with the patient-degree strata of evaluate.py:237-287 (stratify_by_patient_degree): out_bins[n_lab][3][7]
+ * (double) = per lab and per degree group {1-5, 6-15, 16+ observed labs of the pair's patient}: n, sum |r|, sum r^2, sum t,
+ * sum t^2, sum |r / t| over t != 0, count of t != 0, on the winsorised residuals (the reference stratifies after the outlier
+ * guard, evaluate.py:525-530).  degree[N_patient] is torch.bincount(has_lab.edge_index[0]) as int64 (b2g_csr_degrees).
+ * The lab-frequency strata (evaluate.py:290-341) are unions of labs, i.e. sums of rows of `out`. */
+extern "C" int b2g_eval_per_lab_strata(const float* pred, const float* target, const int32_t* rowptr, const int32_t* pair_of,
+                                       const int64_t* patient_idx, const int64_t* degree, int n_lab, int winsorize, float n_sigma,
+                                       double* out, double* out_bins, float* pred_w, void* stream_) {
+  B2G_CHECK_ARG(n_lab >= 0 && (n_lab == 0 || (pred && target && rowptr && pair_of && out && patient_idx && degree && out_bins)) && n_sigma >= 0.f,
+                "eval_per_lab_strata: bad args");
+  if (n_lab == 0) return B2G_OK;
+  k_eval_per_lab<<<(unsigned)n_lab, EV_THREADS, 0, (cudaStream_t)stream_>>>(pred, target, rowptr, pair_of, winsorize, n_sigma, out, pred_w,
+                                                                            patient_idx, degree, out_bins);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

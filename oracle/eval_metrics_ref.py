@@ -75,3 +75,52 @@ def synthetic_case(seed: int = 7, n_pairs: int = 20000, n_labs: int = 50):
     t[lab == 3] = 0.5                                                        # constant targets
     p = (0.6 * t + 0.5 * rng.standard_t(3, size=n_pairs)).astype(np.float32)
     return p, t, lab
+
+
+def synthetic_strata_case(seed: int = 11, n_pairs: int = 20000, n_labs: int = 50, n_patients: int = 700):
+    """Patient index per pair of synthetic_case + a has_lab edge list [2, E] (patient, lab) whose degrees hit every stratum of
+    evaluate.py:268-272 (1-5 / 6-15 / 16+ labs per patient, plus patients with no lab at all) and whose lab counts span the
+    quartile groups of evaluate.py:315-326."""
+    rng = np.random.RandomState(seed)
+    patient = rng.randint(0, n_patients, size=n_pairs).astype(np.int64)
+    deg = np.concatenate([rng.randint(1, 6, n_patients // 3), rng.randint(6, 16, n_patients // 3),
+                          rng.randint(16, n_labs - 1, n_patients - 2 * (n_patients // 3))])
+    deg[:5] = 0
+    weights = np.linspace(1.0, 8.0, n_labs - 1)
+    weights /= weights.sum()
+    src, dst = [], []
+    for p_, d_ in enumerate(deg):
+        if d_ > 0:
+            labs = rng.choice(n_labs - 1, size=int(d_), replace=False, p=weights)
+            src += [p_] * int(d_)
+            dst += labs.tolist()
+    return patient, np.stack([np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)]), n_patients
+
+
+def stratify_by_patient_degree(predictions, targets, patient_indices, has_lab_edge_index, n_patients):
+    """evaluate.py:237-287."""
+    degrees = np.bincount(has_lab_edge_index[0], minlength=n_patients)
+    d = degrees[patient_indices]
+    groups = {"low (1-5 labs)": (d >= 1) & (d <= 5), "medium (6-15 labs)": (d >= 6) & (d <= 15), "high (16+ labs)": d >= 16}
+    out = {}
+    for name, mask in groups.items():
+        if mask.sum() > 0:
+            m = regression_metrics(predictions[mask], targets[mask])
+            m["num_samples"] = int(mask.sum())
+            out[name] = m
+    return out
+
+
+def stratify_by_lab_frequency(predictions, targets, lab_indices, has_lab_edge_index, n_labs):
+    """evaluate.py:290-341."""
+    counts = np.bincount(has_lab_edge_index[1], minlength=n_labs)
+    f = counts[lab_indices]
+    q25, q75 = np.percentile(counts[counts > 0], 25), np.percentile(counts[counts > 0], 75)
+    groups = {"rare (bottom 25%)": f < q25, "common (middle 50%)": (f >= q25) & (f <= q75), "very common (top 25%)": f > q75}
+    out = {}
+    for name, mask in groups.items():
+        if mask.sum() > 0:
+            m = regression_metrics(predictions[mask], targets[mask])
+            m["num_samples"] = int(mask.sum())
+            out[name] = m
+    return out

@@ -1020,6 +1020,17 @@ def test_eval_metrics_match_reference(dev):
             assert float((res["predictions"].cpu() - blob["pred_winsorized"]).abs().max()) <= 2e-5
         else:
             assert res["num_capped"] == 0 and torch.equal(res["predictions"], p)
+    # stratified analysis (evaluate.py:237-341) against what the UNMODIFIED reference functions returned (golden)
+    ei = blob["has_lab_edge_index"].to(dev)
+    deg = torch.bincount(ei[0], minlength=blob["n_patients"])
+    cnt = torch.bincount(ei[1], minlength=blob["n_labs"])
+    res = MX.evaluate_predictions(p, t, lab, blob["n_labs"], patient_indices=blob["patient"].to(dev), patient_lab_degree=deg, lab_counts=cnt)
+    for key in ("by_patient_degree", "by_lab_frequency"):
+        got, want = res["stratified"][key], blob[key]
+        assert list(got) == list(want), (key, list(got), list(want))
+        for grp in want:
+            assert got[grp]["num_samples"] == want[grp]["num_samples"], (key, grp)
+            assert all(close(got[grp][k], want[grp][k], 2e-5) for k in ("mae", "rmse", "r2", "mape")), (key, grp, got[grp], want[grp])
     # run-to-run identical (fixed-order reductions)
     a = MX.evaluate_predictions(p, t, lab, blob["n_labs"])["records"]
     b = MX.evaluate_predictions(p, t, lab, blob["n_labs"])["records"]

@@ -127,3 +127,21 @@ def test_eval_metrics_restatement_matches_reference_functions():
             assert r["num_samples"] == w["num_samples"]
             assert all(close(r[k], w[k]) for k in ("mae", "rmse", "r2", "mape")), (tag, r, w)
     assert 48 not in [r["lab_index"] for r in rows] and 49 not in [r["lab_index"] for r in rows]   # 1-sample / empty labs
+
+
+def test_eval_strata_restatement_matches_reference_golden():
+    """oracle/eval_metrics_ref.stratify_by_* (evaluate.py:237-341) against what the unmodified reference functions returned."""
+    import os
+    import numpy as np
+    from oracle import eval_metrics_ref as E
+    blob = torch.load(os.path.join(os.path.dirname(__file__), "golden", "eval_metrics.pt"), weights_only=False)
+    pw, t, lab = blob["pred_winsorized"].numpy(), blob["target"].numpy(), blob["lab"].numpy()
+    ei, patient = blob["has_lab_edge_index"].numpy(), blob["patient"].numpy()
+    for mine, ref in ((E.stratify_by_patient_degree(pw, t, patient, ei, blob["n_patients"]), blob["by_patient_degree"]),
+                      (E.stratify_by_lab_frequency(pw, t, lab, ei, blob["n_labs"]), blob["by_lab_frequency"])):
+        assert list(mine) == list(ref)
+        for k in ref:
+            assert mine[k]["num_samples"] == ref[k]["num_samples"]
+            for m in ("mae", "rmse", "r2", "mape"):
+                assert abs(mine[k][m] - ref[k][m]) <= 1e-5 * max(1.0, abs(ref[k][m])), (k, m)
+    assert set(blob["by_patient_degree"]) == {"low (1-5 labs)", "medium (6-15 labs)", "high (16+ labs)"}
