@@ -533,6 +533,136 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """--workload C5: BASELINE config 5, inference-only bulk imputation of all held-out (val + test, 30 %) patient-lab pairs on
+    the 100 M-edge graph, 256-d hidden, patients partitioned over the ranks (each rank: a C4s8-shaped share).  One step = one
+    full imputation pass: eval-mode encode + 2 HeteroConv layers (the only exchanges: partial type sums) + the gated decoder
+    over the rank's held-out pairs (inference.py:140-159 recomputes the forward for every call; so does a step).
+    metric: imputed pairs per second, whole job."""
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)
+    ops = importlib.import_module(PKG + ".ops")
+    M = importlib.import_module(PKG + ".model")
+    T = importlib.import_module(PKG + ".trainer")
+    D = importlib.import_module(PKG + ".dist")
+    L = importlib.import_module(PKG + "._lib")
+    lib = L.load()
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=90))
+    share = pkg.synth.SPECS["C4s8"]
+    spec = pkg.synth.GraphSpec("C5s8", share.n_patient, share.n_lab, share.n_dx, share.n_med, share.e_lab, share.e_dx, share.e_med,
+                               share.low_degree_frac, hidden_dim=256)
+    cfg = _cfg(dropout=0.2, loss="mse")
+    cfg["model"]["hidden_dim"] = 256
+    dctx = D.DistContext(device=dev) if world > 1 else None
+    g = pkg.synth.make_graph(spec, seed=42 + rank, device=dev)
+    masker = T.EdgeMasker(g, 0.7, 0.15, 0.15, 0.2, 42 + rank)
+    torch.manual_seed(0)
+    model = M.build_model(cfg, (g.node_types, g.edge_types), None).to(dev)
+    if dctx is not None:
+        model.set_distributed(dctx)
+    model._init_embeddings(g)
+    if world > 1:
+        for name, p in model.named_parameters():
+            if not name.startswith("embeddings.patient"):
+                dist.broadcast(p.data, 0)
+    model.eval()
+    held = (masker.val_mask | masker.test_mask).to(dev)
+    ei = g["patient", "has_lab", "lab"].edge_index
+    pi, li = ei[0][held].contiguous(), ei[1][held].contiguous()
+    n_pairs = int(pi.numel())
+    pi_h, li_h = pi.cpu().pin_memory(), li.cpu().pin_memory()
+    out_h = torch.empty(n_pairs, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            pred = model.predict_lab_values(g, pi, li)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        lib.b2g_reset_launch_count()
+        evs = []
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            pred = model.predict_lab_values(g, pi, li)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        launches = int(lib.b2g_launch_count())
+        tot = torch.tensor([sum(s.elapsed_time(e) for s, e in evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        ms = float(tot.item()) / args.steps
+        # end to end: pair lists from pinned host memory, predictions back to the host
+        pd_, ld_ = torch.empty_like(pi), torch.empty_like(li)
+
+        def e2e_step():
+            pd_.copy_(pi_h, non_blocking=True)
+            ld_.copy_(li_h, non_blocking=True)
+            out_h.copy_(model.predict_lab_values(g, pd_, ld_), non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(n_e2e):
+            e2e_step()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t_e2e.item()) * 1e3 / n_e2e
+    clk = clocks.stop() if rank == 0 else None
+    n_all = torch.tensor([n_pairs], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_all)
+        if dctx.peer is not None:
+            dctx.peer.check()
+    if rank == 0:
+        total_pairs = int(n_all.item())
+        e_und = spec.e_lab + spec.e_dx + spec.e_med
+        d = 256
+        bytes_min = NUM_LAYERS * (2 * spec.n_patient * d * 4 + e_und * 4 + 3 * (spec.n_patient + 1) * 4) + n_pairs * (16 + 4)
+        peaks = _peaks()
+        line = {"metric": "bulk_imputation_pairs_per_sec", "value": total_pairs / (ms * 1e-3), "unit": "imputed (patient, lab) pairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (large-M linears with <= 227 KB of weights: TF32 operands on tcgen05)", "data": "synthetic",
+                "config": {"workload": f"C5 (BASELINE configs[4]): eval-mode bulk imputation, d=256, L=2; per GPU {spec.n_patient} patients, "
+                                       f"{spec.e_lab}/{spec.e_dx}/{spec.e_med} edges, {n_pairs} held-out (val+test) pairs; x{world} GPUs = "
+                                       f"{total_pairs} pairs" + (" = the 100 M-edge graph" if world == 8 else ""),
+                           "step": "HeteroRGCN.predict_lab_values in eval mode, node embeddings recomputed every step (no cache)",
+                           "l2": "flushed with a 256 MiB write before every timed step", "parallelism": (f"patient-partitioned x{world}, the only "
+                           f"exchanges are the per-layer partial type sums" if world > 1 else "single GPU")},
+                "e2e": {"value": total_pairs / (e2e_ms * 1e-3), "unit": "imputed (patient, lab) pairs/s", "ms_per_step": e2e_ms, "steps": n_e2e,
+                        "h2d_bytes_per_step": 16 * n_pairs, "d2h_bytes_per_step": 4 * n_pairs},
+                "gpu_launches": launches, "clocks": clk,
+                "roofline": {"bound": "hbm", "kernel": "whole imputation pass", "achieved": bytes_min / (ms * 1e-3) / 1e9, "peak": peaks["hbm"],
+                             "unit": "GB/s", "frac": bytes_min / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                             "algorithmic_bytes": bytes_min, "what": "compulsory traffic of the pass: per layer read x_p + write out_p + adjacency "
+                             "once, plus the pair list and the predictions (SURVEY.md 8d, forward half)"}}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def a_share(ms, tot):
     return round(ms / tot, 4) if tot > 0 else None
 
@@ -551,6 +681,8 @@ def main():
         run_reference(args)
     elif args.impl == "torch_gpu":
         run_torch_gpu(args)
+    elif args.workload == "C5":
+        run_c5(args)
     else:
         if args.warmup < 3:
             args.warmup = 3

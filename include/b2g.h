@@ -73,6 +73,19 @@ int b2g_csr_chunk_count(const int32_t* rowptr, int64_t n_rows, int32_t chunk, in
 int b2g_csr_chunk_fill(const int32_t* rowptr, int64_t n_rows, int32_t chunk, const int32_t* row_item_ptr,
                        int32_t* item_row, int32_t* item_start, void* stream);
 
+/* (a') graph ingest -- replaces the per-row Python loops of graph_build.py:476-586.
+ * out[i] = index[j] where sorted_ids[j] == query[i], or -1: NodeIndexer.get_index (graph_build.py:84-89) for every table row;
+ * sorted_ids int64[n_dict] ascending and distinct, index int32[n_dict] the node index of each id. */
+int b2g_id_lookup(const int64_t* sorted_ids, const int32_t* index, int64_t n_dict, const int64_t* query, int64_t m,
+                  int32_t* out, void* stream);
+/* SYNC.  Rows i with src_idx[i] >= 0 and dst_idx[i] >= 0 become edges IN ROW ORDER (graph_build.py:502-508: rows with an unknown
+ * entity are dropped): edge_index[e] = src_idx[i], edge_index[*h_n_edges + e] = dst_idx[i] (int64; the caller's buffer holds
+ * 2 m entries, the result is the [2, E] tensor of graph_build.py:515 in its first 2 E entries), attr_out[e] = attr[i]
+ * (optional), row_of_edge[e] = i (optional).  ws: b2g_edges_from_rows_ws_bytes(m). */
+size_t b2g_edges_from_rows_ws_bytes(int64_t m);
+int b2g_edges_from_rows(const int32_t* src_idx, const int32_t* dst_idx, const float* attr, int64_t m, int64_t* edge_index,
+                        float* attr_out, int64_t* row_of_edge, int64_t* h_n_edges, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (b) message passing -- replaces SAGEConv.propagate: index_select + scatter_add + /clamp(count,1)
  *     (PyG sage_conv.py / utils/scatter.py; call sites model.py:125-131,256)

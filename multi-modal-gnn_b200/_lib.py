@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb2g.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["graph.cu", "spmm.cu", "dense.cu", "norm.cu", "decoder.cu", "dense_tc.cu", "layer_tc.cu"]
+SOURCES = ["graph.cu", "spmm.cu", "dense.cu", "norm.cu", "decoder.cu", "dense_tc.cu", "layer_tc.cu", "ingest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -163,6 +163,9 @@ _PROTOS = {
                                 _P, _P, _P, c_size_t, _P]),
     "b2g_decoder_bwd_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, c_uint64, _P, _P, _P, _P,
                                    _P, _P, _P, c_size_t, _P]),
+    "b2g_id_lookup": (c_int, [_P, _P, c_int64, _P, c_int64, _P, _P]),
+    "b2g_edges_from_rows_ws_bytes": (c_size_t, [c_int64]),
+    "b2g_edges_from_rows": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, ctypes.POINTER(c_int64), _P, c_size_t, _P]),
     "b2g_adj_bits_build": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P]),
     "b2g_layer_cat_weights": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, ctypes.POINTER(c_void_p), c_int, _P, c_int, c_int,
                                       ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int),

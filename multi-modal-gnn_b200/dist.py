@@ -298,6 +298,42 @@ def partition_graph(data, world: int, rank: int, sharded_type: str = "patient") 
     return g, info
 
 
+class PairRoute:
+    """Routing of arbitrary GLOBAL (patient, lab) prediction pairs to the ranks that own the patients ("pairs are
+    routed to the GPU owning the patient"; bulk imputation, BASELINE config 5) and of the predictions back to the asking rank.
+
+        route = PairRoute(patient_idx_global, lab_idx, bounds, dctx)     # all-to-all of the index lists
+        pred_local = model.predict_lab_values(local_graph, route.patient_local, route.lab_local)
+        pred = route.gather_back(pred_local)                             # same order as the caller's pair list
+    """
+
+    def __init__(self, patient_idx: torch.Tensor, lab_idx: torch.Tensor, bounds: torch.Tensor, dctx: DistContext):
+        self.dctx = dctx
+        world, dev = dctx.world, patient_idx.device
+        b = bounds.to(dev)
+        owner = torch.bucketize(patient_idx, b[1:-1].contiguous(), right=True)            # rank whose [b[r], b[r+1]) holds the patient
+        order = torch.argsort(owner, stable=True)
+        self.order = order
+        self.send_counts = torch.bincount(owner, minlength=world)
+        recv_counts = torch.empty_like(self.send_counts)
+        dist.all_to_all_single(recv_counts, self.send_counts, group=dctx.group)
+        self.recv_counts = recv_counts
+        sc, rc = self.send_counts.tolist(), recv_counts.tolist()
+        self._sc, self._rc = sc, rc
+        payload = torch.stack([patient_idx[order], lab_idx[order]], 1).contiguous()        # [n, 2] int64
+        got = torch.empty((sum(rc), 2), dtype=payload.dtype, device=dev)
+        dist.all_to_all_single(got, payload, output_split_sizes=rc, input_split_sizes=sc, group=dctx.group)
+        self.patient_local = (got[:, 0] - b[dctx.rank]).contiguous()
+        self.lab_local = got[:, 1].contiguous()
+
+    def gather_back(self, pred_local: torch.Tensor) -> torch.Tensor:
+        back = torch.empty(sum(self._sc), dtype=pred_local.dtype, device=pred_local.device)
+        dist.all_to_all_single(back, pred_local.contiguous(), output_split_sizes=self._sc, input_split_sizes=self._rc, group=self.dctx.group)
+        out = torch.empty_like(back)
+        out[self.order] = back
+        return out
+
+
 def globalize_degrees(graph_index, dctx: DistContext):
     """Mean aggregation onto replicated node types divides by the GLOBAL neighbour count: all-reduce the per-type-node
     degrees once and overwrite the local CSR's deg / inv_deg (integer all-reduce: exact)."""

@@ -272,3 +272,33 @@ def test_partitioned_step_equals_single_process_gloo(world):
     """world 3: an odd split, so the partitions are of unequal size and the middle rank has two neighbours."""
     out = _spawn(_partitioned_step, world, 4)
     assert len(out) == world and max(out.values()) <= 2e-3
+
+
+def _route(rank, world):
+    D = importlib.import_module(PKG + ".dist")
+    dctx = D.DistContext()
+    bounds = torch.tensor([0, 10, 25, 40][:world + 1] if world == 3 else [0, 17, 40])
+    gen = torch.Generator().manual_seed(100 + rank)
+    n = 50 + 7 * rank
+    pi = torch.randint(0, int(bounds[-1]), (n,), generator=gen)
+    li = torch.randint(0, 9, (n,), generator=gen)
+    route = D.PairRoute(pi, li, bounds, dctx)
+    p0, p1 = int(bounds[rank]), int(bounds[rank + 1])
+    assert bool(((route.patient_local >= 0) & (route.patient_local < p1 - p0)).all()), "every routed pair belongs to this rank's range"
+    # the owner "predicts" f(global patient, lab); the asking rank gets the values back in ITS order
+    pred_local = ((route.patient_local + p0) * 1000 + route.lab_local).double()
+    back = route.gather_back(pred_local)
+    assert torch.equal(back, (pi * 1000 + li).double())
+    # totals are conserved
+    tot = torch.tensor([int(route.patient_local.numel()), n])
+    dist.all_reduce(tot)
+    assert int(tot[0]) == int(tot[1])
+    return True
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pair_routing_to_owner_ranks(world):
+    """Bulk imputation (BASELINE config 5): arbitrary global (patient, lab) pairs reach the rank owning the patient and the
+    predictions return in the caller's order (gloo all-to-all on the CPU)."""
+    res = _spawn(_route, world)
+    assert all(res.values())

@@ -264,3 +264,52 @@ def test_whole_training_step_on_C2_matches_oracle(mode):
             assert max(n_gpu.values()) <= 8e-2, max(n_gpu, key=n_gpu.get)
     finally:
         ops.set_precision(old)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_bulk_imputation_hidden_256_matches_oracle(mode):
+    """BASELINE config 5 (inference-only bulk imputation, 256-d hidden; inference.py:140-159, advanced_visualizations.py:439-461):
+    eval-mode predictions for the held-out (val + test) pairs and for every never-measured pair of a patient range, d = 256,
+    against the oracle on a graph with both gate branches."""
+    pkg, G, ops, M, T, MET = _mods()
+    dev = torch.device("cuda:0")
+    old = ops.PRECISION
+    ops.set_precision(mode)
+    try:
+        spec = pkg.synth.GraphSpec("c5-small", 3000, 50, 114, 100, 90000, 8000, 24000, 0.1, hidden_dim=256)
+        g = pkg.synth.make_graph(spec, seed=6)
+        counts = {nt: int(g[nt].num_nodes) for nt in g.node_types}
+        ets = list(g.edge_types)
+        sd = R.init_state(counts, ets, hidden=256, seed=21)
+        for k in list(sd):                       # non-trivial running statistics (eval mode uses them)
+            if k.endswith("running_mean"):
+                sd[k] = torch.randn_like(sd[k]) * 0.1
+            if k.endswith("running_var"):
+                sd[k] = torch.rand_like(sd[k]) + 0.5
+        cfg = _cfg(0.2)
+        cfg["model"]["hidden_dim"] = 256
+        model = M.build_model(cfg, (g.node_types, g.edge_types), None).to(dev)
+        gd = pkg.synth.make_graph(spec, seed=6).to(dev)
+        model._init_embeddings(gd)
+        model.load_state_dict(sd)
+        model.eval()
+        ei = g["patient", "has_lab", "lab"].edge_index
+        _, va, te = R.split_masks(ei.shape[1])
+        held = va | te
+        pi, li = ei[0][held], ei[1][held]
+        with torch.no_grad():
+            pred = model.predict_lab_values(gd, pi.to(dev), li.to(dev))
+            ref = R.predict_lab_values(sd, counts, ets, g.edge_index_dict, pi, li, False)
+            some = torch.arange(100, 160)
+            mp, ml, mv = model.impute_missing(gd, some.to(dev))
+            ref_m = R.predict_lab_values(sd, counts, ets, g.edge_index_dict, mp.cpu(), ml.cpu(), False)
+        deg = torch.bincount(ei[0], minlength=counts["patient"])
+        assert bool((deg[pi] < 6).any()) and bool((deg[pi] >= 6).any()), "both heads must be exercised"
+        have = set(zip(ei[0].tolist(), ei[1].tolist()))
+        assert list(zip(mp.tolist(), ml.tolist())) == [(p, l) for p in some.tolist() for l in range(counts["lab"]) if (p, l) not in have]
+        tol = 1e-4 if mode == "fp32" else 1e-2
+        e1, e2 = relerr(pred, ref), relerr(mv, ref_m)
+        print(f"[config 5, d=256, {mode}] held-out pairs {pi.numel()}: max-rel {e1:.2e}; never-measured pairs {mp.numel()}: max-rel {e2:.2e}")
+        assert e1 <= tol and e2 <= tol
+    finally:
+        ops.set_precision(old)

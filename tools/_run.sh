@@ -1,5 +1,3 @@
-python tools/layer_bench.py --workload C4s8 --reps 1 --only-layer > gpurun_out/lb_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_layer_traffic_c4s8.csv python tools/layer_bench.py --workload C4s8 --reps 1 --only-layer > gpurun_out/ncu_traffic.log 2>&1
-python tools/layer_bench.py --workload C4s8 --reps 1 > gpurun_out/lb_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"k_layer_tf32|k_adjT_tf32" -c 6 -o gpurun_out/r2_ncu_layer_kernels python tools/layer_bench.py --workload C4s8 --reps 1 > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_traffic.log gpurun_out/ncu_full.log; wc -l gpurun_out/r2_layer_traffic_c4s8.csv
+python -m pytest tests/test_gpu_ingest.py tests/test_gpu_e2e_parity.py::test_bulk_imputation_hidden_256_matches_oracle tests/test_gpu_parity.py::test_eval_metrics_match_reference -q -m gpu -s 2>&1 | grep -v Warning | grep "^\[\|passed\|failed\|Error\|error\|assert" | head -30
+python bench.py --workload C5 --steps 5 > gpurun_out/r2_bench_c5_1gpu.json 2> gpurun_out/r2_bench_c5_1gpu.err; echo "bench C5 rc=$?"; tail -c 1500 gpurun_out/r2_bench_c5_1gpu.err | grep -v Warning | tail -5
+cut -c1-900 gpurun_out/r2_bench_c5_1gpu.json
