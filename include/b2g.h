@@ -169,11 +169,14 @@ int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* bias, const
  *   backward: x = dout_patient, rscale_r = 1/deg_r(patient) -> dY_r
  * with_colsum = 1: `out` has 32 more rows, [32 (nw + 1), 128], and row 32 nw holds the column sums of x (the bias gradient
  * when x = dout) -- one constant column of ones appended to the expanded adjacency; col_scale then has 32 (nw + 1) entries.
- * ws: b2g_layer_adjT_tc_ws_bytes(nw + with_colsum).  Supported for d = 128 and nw + with_colsum <= 16. */
+ * dense_b / dense_out (both or neither): dense_out[128, 128] = x^T . dense_b[m, 128] in the same pass (backward:
+ * dW_root[out, in] = dout^T x_patient), i.e. D = x^T [dense_b | diag(rscale) A | 1] with one read of x.
+ * ws: b2g_layer_adjT_tc_ws_bytes(nw + with_colsum).  Supported for d = 128 and 128 [dense_b] + 32 (nw + with_colsum) <= 512. */
 int b2g_layer_adjT_tc_supported(int64_t m, int d, int nw);
 size_t b2g_layer_adjT_tc_ws_bytes(int nw);
 int b2g_layer_adjT_tc(const float* x, const uint32_t* bits, const b2g_bit_layout_t* h_layout, const float* const* h_rscale,
-                      const float* col_scale, int64_t m, int with_colsum, float* out, void* ws, size_t ws_bytes, void* stream);
+                      const float* col_scale, int64_t m, int with_colsum, const float* dense_b, float* dense_out, float* out,
+                      void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (c) embedding tables -- nn.Embedding(arange(N)) fwd / dense grad (model.py:225-226)

@@ -176,7 +176,7 @@ _PROTOS = {
                                  c_size_t, _P]),
     "b2g_layer_adjT_tc_supported": (c_int, [c_int64, c_int, c_int]),
     "b2g_layer_adjT_tc_ws_bytes": (c_size_t, [c_int]),
-    "b2g_layer_adjT_tc": (c_int, [_P, _P, ctypes.POINTER(BitLayoutT), ctypes.POINTER(c_void_p), _P, c_int64, c_int, _P, _P, c_size_t, _P]),
+    "b2g_layer_adjT_tc": (c_int, [_P, _P, ctypes.POINTER(BitLayoutT), ctypes.POINTER(c_void_p), _P, c_int64, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "b2g_loss_ws_bytes": (c_size_t, [c_int64]),
     "b2g_weighted_loss": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
 }

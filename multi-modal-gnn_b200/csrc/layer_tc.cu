@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
   __shared__ __align__(8) uint64_t bar_full[LY_MAX_STAGES], bar_empty[LY_MAX_STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ double s_stat[4][2][32];
-  __shared__ uint4 s_lut[16];                          // nibble -> four {0 | ~0} masks
+  __shared__ uint4 s_lut[16];                          // nibble -> four {0 | ~0} masks (a byte table + PRMT costs more ALU than it saves)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 16)
@@ -220,9 +220,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
               uint8_t* arow = abase + r * 128;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                uint4 m4 = s_lut[(wc[i] >> (4 * j)) & 15u];
-                m4.x &= sac[i]; m4.y &= sac[i]; m4.z &= sac[i]; m4.w &= sac[i];
-                *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) = m4;
+                const uint4 m4 = s_lut[(wc[i] >> (4 * j)) & 15u];
+                *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) = make_uint4(m4.x & sac[i], m4.y & sac[i], m4.z & sac[i], m4.w & sac[i]);
               }
             }
           } else {
@@ -360,12 +359,14 @@ struct AdjTParams {
   const uint32_t* bits;
   const float* rscale[LY_MAXREL];
   BitLayout bl;
-  float* partial;                      // [grid][128][nb]
+  float* partial;                      // [grid][128][dcols]
   int64_t m;
-  int nb;                              // 32 * (nw + ones)
+  int nb;                              // 32 * (nw + ones): expanded adjacency (+ ones) columns
+  int xb;                              // 1: a dense [m, 128] matrix (second tensor map) supplies 128 more columns IN FRONT: D = X^T [Xb | A | 1]
+  int dcols;                           // 128 * xb + nb
   int tmem_cols;
   int xstages;
-  int ones;                            // 1: one more 32-column block whose first column is 1 -> row 32 nw of the output = column sums of X
+  int ones;                            // 1: one more 32-column block whose first column is 1 -> column sums of X
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn32(uint32_t smem_addr) {
@@ -378,8 +379,9 @@ __device__ __forceinline__ uint64_t make_desc_mn32(uint32_t smem_addr) {
   return d;
 }
 
-// dynamic smem (1024-byte aligned): X ring [xstages][4 sub-tiles x 4 KB] | adjacency ring [2][nw sub-tiles x 4 KB]
+// dynamic smem (1024-byte aligned): X ring [xstages][(4 + 4 xb) sub-tiles x 4 KB] | adjacency ring [2][(nw + ones) sub-tiles x 4 KB]
 __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_constant__ CUtensorMap map_x,
+                                                             const __grid_constant__ CUtensorMap map_b,
                                                              const __grid_constant__ AdjTParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_xfull[AT_MAX_XSTAGES], bar_xempty[AT_MAX_XSTAGES], bar_bfull[AT_BSTAGES], bar_bempty[AT_BSTAGES],
@@ -388,9 +390,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = prm.bl.nw;
   const uint32_t a_bytes = 4u * AT_SUB;                                // 128 columns of X
+  const uint32_t xs_bytes = a_bytes * (1u + (uint32_t)prm.xb);         // one X-ring stage: X (and Xb)
   const uint32_t b_bytes = (uint32_t)(nw + prm.ones) * AT_SUB;
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-  uint8_t* bbase = base + (size_t)prm.xstages * a_bytes;
+  uint8_t* bbase = base + (size_t)prm.xstages * xs_bytes;
   if (prm.ones && warp == 3) {
     // constant block: element (row r, column 0) = 1 (32-byte chunk 0 of row r sits at chunk r & 3), everything else 0.
     // Rows beyond m contribute nothing: TMA zero-fills the matching X rows.
@@ -433,22 +436,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
       uint32_t ph = 1;
       for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         mbar_wait(&bar_xempty[s], ph);
-        mbar_expect_tx(&bar_xfull[s], a_bytes);
-        uint8_t* st = base + (size_t)s * a_bytes;
+        mbar_expect_tx(&bar_xfull[s], xs_bytes);
+        uint8_t* st = base + (size_t)s * xs_bytes;
         for (int c = 0; c < 4; ++c) tma_load_2d(st + c * AT_SUB, &map_x, &bar_xfull[s], c * KB, (int)(t * AT_ROWS));
+        if (prm.xb)
+          for (int c = 0; c < 4; ++c) tma_load_2d(st + a_bytes + c * AT_SUB, &map_b, &bar_xfull[s], c * KB, (int)(t * AT_ROWS));
         if (++s == nxs) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // D rows = the 128 columns of X; N is split into pieces of <= 256 columns, one MMA each per 8 reduction rows.
+    // D rows = the 128 columns of X; N is split into pieces of <= 256 columns, one MMA each per 8 reduction rows:
+    // [Xb (128 columns, from the X ring)] [adjacency columns 0..255] [the rest].
     // One thread runs the loop; stage / phase counters are incremental and descriptors are formed by addition.
     if (elect_one()) {
       const int n1 = prm.nb > 256 ? 256 : prm.nb, n2 = prm.nb - n1;
+      const uint32_t off0 = 128u * (uint32_t)prm.xb;
+      const uint32_t idesc0 = make_idesc(128) | (1u << 15) | (1u << 16);
       const uint32_t idesc1 = make_idesc(n1) | (1u << 15) | (1u << 16);
       const uint32_t idesc2 = make_idesc(n2 > 0 ? n2 : 16) | (1u << 15) | (1u << 16);
       const uint64_t dhi = make_desc_mn32(0);
       const uint32_t xa = smem_u32(base) >> 4, ba = smem_u32(bbase) >> 4;
-      const uint32_t a16 = a_bytes >> 4, b16 = b_bytes >> 4;
+      const uint32_t x16 = xs_bytes >> 4, a16 = a_bytes >> 4, b16 = b_bytes >> 4;
       int sx = 0, sb_ = 0;
       uint32_t phx = 0, phb = 0;
       bool first = true;
@@ -456,12 +464,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
         mbar_wait(&bar_xfull[sx], phx);
         mbar_wait(&bar_bfull[sb_], phb);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = dhi + (xa + (uint32_t)sx * a16);
+        const uint64_t da = dhi + (xa + (uint32_t)sx * x16);
         const uint64_t db = dhi + (ba + (uint32_t)sb_ * b16);
 #pragma unroll
         for (int j = 0; j < AT_ROWS / 8; ++j) {          // 8 reduction rows = 1024 B = 64 descriptor units
-          umma_tf32(tmem_base, da + 64 * j, db + 64 * j, idesc1, !(first && j == 0));
-          if (n2 > 0) umma_tf32(tmem_base + 256, da + 64 * j, db + (8 * AT_SUB >> 4) + 64 * j, idesc2, !(first && j == 0));
+          const uint32_t acc = !(first && j == 0);
+          if (prm.xb) umma_tf32(tmem_base, da + 64 * j, da + a16 + 64 * j, idesc0, acc);
+          umma_tf32(tmem_base + off0, da + 64 * j, db + 64 * j, idesc1, acc);
+          if (n2 > 0) umma_tf32(tmem_base + off0 + 256, da + 64 * j, db + (8 * AT_SUB >> 4) + 64 * j, idesc2, acc);
         }
         first = false;
         umma_commit(&bar_xempty[sx]);
@@ -509,8 +519,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                // 32-byte chunk j (8 columns) at chunk j ^ (row & 3)
               uint8_t* dst = brow + ((j ^ (lane & 3)) << 5);
-              *reinterpret_cast<uint4*>(dst) = expand4(word, 8 * j, sa);
-              *reinterpret_cast<uint4*>(dst + 16) = expand4(word, 8 * j + 4, sa);
+              *reinterpret_cast<uint4*>(dst) = expand4(word, 8 * j, sa);        // (ALU expansion: a shared-memory look-up table, as in
+              *reinterpret_cast<uint4*>(dst + 16) = expand4(word, 8 * j + 4, sa);   //  k_layer_tf32, measured 25 % slower in this kernel)
             }
           } else {
             const uint32_t sb = __float_as_uint(pick_scale(scur, prm.bl.rel_b[k]));
@@ -541,9 +551,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
     mbar_wait(&bar_done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = q * 32 + lane;                                   // row of D = column of X
-    float* dst_row = prm.partial + ((size_t)blockIdx.x * 128 + row) * prm.nb;
+    float* dst_row = prm.partial + ((size_t)blockIdx.x * 128 + row) * prm.dcols;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < prm.nb; c0 += 32) {
+    for (int c0 = 0; c0 < prm.dcols; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(taddr + c0, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -560,12 +570,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
   }
 }
 
-// out[c, r] = cscale[c] * sum over CTAs (fixed order) of partial[cta][r][c]      partial records are [128][nb]
-__global__ void __launch_bounds__(256) k_adjT_reduce(const float* __restrict__ partial, int n_cta, int nb, const float* __restrict__ cscale,
-                                                     float* __restrict__ out) {
+// per-CTA records [128][dcols] added in fixed order; columns [0, off0) go to out_w[128][off0] as they are (X^T Xb = a weight
+// gradient dW[out, in]), columns off0.. are written transposed and scaled: out_t[c - off0][r] = cscale[c - off0] * sum
+__global__ void __launch_bounds__(256) k_adjT_reduce(const float* __restrict__ partial, int n_cta, int dcols, int off0,
+                                                     const float* __restrict__ cscale, float* __restrict__ out_t, float* __restrict__ out_w) {
   __shared__ float4 sh[8][32];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int n4 = 128 * nb / 4;
+  const int n4 = 128 * dcols / 4;
   const int i4 = blockIdx.x * 32 + lane;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i4 < n4) {
@@ -584,13 +595,18 @@ __global__ void __launch_bounds__(256) k_adjT_reduce(const float* __restrict__ p
     const float4 v = sh[k][lane];
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  const int i = i4 * 4, r = i / nb, cc = i % nb;             // nb % 4 == 0: the 4 outputs share row r
+  const int i = i4 * 4, r = i / dcols, cc = i % dcols;       // dcols % 4 == 0: the 4 outputs share row r
+  if (cc < off0) {
+    *reinterpret_cast<float4*>(out_w + (size_t)r * off0 + cc) = acc;
+    return;
+  }
+  const int ct = cc - off0;
   float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (cscale) sc = __ldg(reinterpret_cast<const float4*>(cscale + cc));
-  out[(size_t)cc * 128 + r] = acc.x * sc.x;
-  out[(size_t)(cc + 1) * 128 + r] = acc.y * sc.y;
-  out[(size_t)(cc + 2) * 128 + r] = acc.z * sc.z;
-  out[(size_t)(cc + 3) * 128 + r] = acc.w * sc.w;
+  if (cscale) sc = __ldg(reinterpret_cast<const float4*>(cscale + ct));
+  out_t[(size_t)ct * 128 + r] = acc.x * sc.x;
+  out_t[(size_t)(ct + 1) * 128 + r] = acc.y * sc.y;
+  out_t[(size_t)(ct + 2) * 128 + r] = acc.z * sc.z;
+  out_t[(size_t)(ct + 3) * 128 + r] = acc.w * sc.w;
 }
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------------
@@ -651,12 +667,20 @@ __global__ void __launch_bounds__(256) k_cat_weights(const __grid_constant__ Cat
 }
 
 // sums[2n] (fp64) = per-CTA records [n_cta][2][n] added in CTA order
-__global__ void k_stats_reduce(const double* __restrict__ rec, int n_cta, int n2, double* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n2) return;
+__global__ void __launch_bounds__(256) k_stats_reduce(const double* __restrict__ rec, int n_cta, int n2, double* __restrict__ sums) {
+  __shared__ double sh[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   double a = 0.0;
-  for (int c = 0; c < n_cta; ++c) a += rec[(size_t)c * n2 + i];
-  sums[i] = a;
+  if (i < n2)
+    for (int c = slice; c < n_cta; c += 8) a += rec[(size_t)c * n2 + i];       // 8 interleaved slices of the CTA records ...
+  sh[slice][lane] = a;
+  __syncthreads();
+  if (slice == 0 && i < n2) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) a += sh[k][lane];                                // ... combined in fixed order
+    sums[i] = a;
+  }
 }
 
 int fill_layout(BitLayout* bl, const b2g_bit_layout_t* h) {
@@ -787,52 +811,60 @@ extern "C" int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* 
             "exp(w8) wait-empty(adj) %lld wait-empty(x) %lld\n", h[0 * 4 + 2], h[0], h[1 * 4], h[1 * 4 + 1], h[4 * 4], h[8 * 4], h[8 * 4 + 1]);
   }
   if (stat_sums) {
-    k_stats_reduce<<<(unsigned)ceil_div(2 * n, 128), 128, 0, st>>>(prm.stats, grid, 2 * n, stat_sums);
+    k_stats_reduce<<<(unsigned)ceil_div(2 * n, 32), 256, 0, st>>>(prm.stats, grid, 2 * n, stat_sums);
     B2G_LAUNCH_CHECK();
   }
   return B2G_OK;
 }
 
 namespace {
-inline int adjT_xstages(int nw) {
-  const size_t left = 224 * 1024 - (size_t)AT_BSTAGES * nw * AT_SUB;
-  int xs = (int)(left / (4 * (size_t)AT_SUB));
+inline int adjT_xstages(int nsub, int xb) {
+  const size_t left = 224 * 1024 - (size_t)AT_BSTAGES * nsub * AT_SUB;
+  int xs = (int)(left / ((size_t)(4 + 4 * xb) * AT_SUB));
   return xs > AT_MAX_XSTAGES ? AT_MAX_XSTAGES : xs;
 }
 }  // namespace
+/* supported: d = 128 and 128 * with_dense + 32 * (nw + with_colsum) <= 512 TMEM columns */
 extern "C" int b2g_layer_adjT_tc_supported(int64_t m, int d, int nw) {
   if (m < 1 || d != 128 || nw < 1 || nw > 16) return 0;        // D = [128, 32 nw] fp32 must fit the 512 TMEM columns
-  return adjT_xstages(nw) >= 2 ? 1 : 0;
+  return adjT_xstages(nw, 0) >= 2 ? 1 : 0;
 }
-extern "C" size_t b2g_layer_adjT_tc_ws_bytes(int nw) { return (size_t)sm_count() * 128 * 32 * nw * 4 + 256; }
+extern "C" size_t b2g_layer_adjT_tc_ws_bytes(int nw) { return (size_t)sm_count() * 128 * (128 + 32 * (size_t)nw) * 4 + 256; }
 
 extern "C" int b2g_layer_adjT_tc(const float* x, const uint32_t* bits, const b2g_bit_layout_t* h_layout, const float* const* h_rscale,
-                                 const float* col_scale, int64_t m, int with_colsum, float* out, void* ws, size_t ws_bytes, void* stream_) {
+                                 const float* col_scale, int64_t m, int with_colsum, const float* dense_b, float* dense_out,
+                                 float* out, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(x && bits && out && h_layout && b2g_layer_adjT_tc_supported(m, 128, h_layout->nw), "layer_adjT_tc: unsupported shape");
   B2G_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(ws) && (!col_scale || aligned16(col_scale)), "layer_adjT_tc: unaligned pointer");
+  B2G_CHECK_ARG((dense_b == nullptr) == (dense_out == nullptr) && aligned16(dense_b) && aligned16(dense_out), "layer_adjT_tc: dense_b / dense_out");
   AdjTParams prm{};
   int rc = fill_layout(&prm.bl, h_layout);
   if (rc) return rc;
   const int nw = prm.bl.nw;
   prm.ones = with_colsum ? 1 : 0;
-  B2G_CHECK_ARG(nw + prm.ones <= 16, "layer_adjT_tc: 32 (nw + 1) output columns exceed the 512 TMEM columns");
-  const int nb = 32 * (nw + prm.ones);
-  if (!ws || ws_bytes < b2g_layer_adjT_tc_ws_bytes(nw + prm.ones)) {
+  prm.xb = dense_b ? 1 : 0;
+  const int nsub = nw + prm.ones;
+  const int nb = 32 * nsub;
+  prm.dcols = 128 * prm.xb + nb;
+  B2G_CHECK_ARG(prm.dcols <= 512, "layer_adjT_tc: %d output columns exceed the 512 TMEM columns", prm.dcols);
+  if (!ws || ws_bytes < b2g_layer_adjT_tc_ws_bytes(nsub)) {
     set_error("layer_adjT_tc: workspace too small");
     return B2G_EWS;
   }
-  CUtensorMap map_x;
+  CUtensorMap map_x, map_b;
   rc = make_map(&map_x, x, m, 128, AT_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  rc = make_map(&map_b, dense_b ? dense_b : x, m, 128, AT_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
   prm.bits = bits; prm.partial = (float*)ws; prm.m = m; prm.nb = nb;
   for (int r = 0; r < LY_MAXREL; ++r) prm.rscale[r] = h_rscale ? h_rscale[r] : nullptr;
   int cols = 32;
-  while (cols < nb) cols <<= 1;
+  while (cols < prm.dcols) cols <<= 1;
   prm.tmem_cols = cols;
-  prm.xstages = adjT_xstages(nw + prm.ones);
+  prm.xstages = adjT_xstages(nsub, prm.xb);
   B2G_CHECK_ARG(prm.xstages >= 2, "layer_adjT_tc: shared memory too small for nw=%d", nw);
-  const size_t smem = (size_t)prm.xstages * 4 * AT_SUB + (size_t)AT_BSTAGES * (nw + prm.ones) * AT_SUB + 1024;
+  const size_t smem = (size_t)prm.xstages * (4 + 4 * prm.xb) * AT_SUB + (size_t)AT_BSTAGES * nsub * AT_SUB + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     B2G_CUDA(cudaFuncSetAttribute(k_adjT_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -840,9 +872,9 @@ extern "C" int b2g_layer_adjT_tc(const float* x, const uint32_t* bits, const b2g
   }
   int64_t tiles = ceil_div(m, AT_ROWS);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  k_adjT_tf32<<<grid, AT_THREADS, smem, st>>>(map_x, prm);
+  k_adjT_tf32<<<grid, AT_THREADS, smem, st>>>(map_x, map_b, prm);
   B2G_LAUNCH_CHECK();
-  k_adjT_reduce<<<(unsigned)ceil_div(128 * nb / 4, 32), 256, 0, st>>>(prm.partial, grid, nb, col_scale, out);
+  k_adjT_reduce<<<(unsigned)ceil_div(128 * prm.dcols / 4, 32), 256, 0, st>>>(prm.partial, grid, prm.dcols, 128 * prm.xb, col_scale, out, dense_out);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

@@ -826,18 +826,24 @@ def layer_fwd_tc_(x, wcat, bias, bits, pb, rscales, y, stat_sums=None):
     return y
 
 
-def layer_adjT_tc_(x, bits, pb, rscales, col_scale, with_colsum=False):
-    """[32 nw, 128] = col_scale * (diag(rscale) A)^T x;  with_colsum: 32 more rows, row 32 nw = column sums of x"""
+def layer_adjT_tc_(x, bits, pb, rscales, col_scale, with_colsum=False, dense_b=None):
+    """[32 nw, 128] = col_scale * (diag(rscale) A)^T x;  with_colsum: 32 more rows, row 32 nw = column sums of x;
+    dense_b [m, 128]: additionally returns x^T dense_b [128, 128] from the same pass (-> (out, x^T dense_b))"""
     lib = _lib.load()
     m = x.shape[0]
     nsub = pb.nw + (1 if with_colsum else 0)
     out = torch.empty((32 * nsub, 128), dtype=torch.float32, device=x.device)
+    dw = torch.empty((128, 128), dtype=torch.float32, device=x.device) if dense_b is not None else None
     ws = workspace(lib.b2g_layer_adjT_tc_ws_bytes(nsub), x.device)
-    cost(4 * m * 128 + 4 * m * pb.nw + 4 * out.numel(), 2 * m * 128 * 32 * nsub)
+    cost(4 * m * 128 * (2 if dense_b is not None else 1) + 4 * m * pb.nw + 4 * out.numel(), 2 * m * 128 * (32 * nsub + (128 if dense_b is not None else 0)))
     _run("b2g_layer_adjT_tc", lib.b2g_layer_adjT_tc, x.data_ptr(), bits.data_ptr(), ctypes.byref(pb.layout),
-         _ptr_array(list(rscales) + [None] * (4 - len(rscales))), _ptr(col_scale), m, int(bool(with_colsum)), out.data_ptr(), ws.data_ptr(),
-         ws.numel(), _stream())
-    return out
+         _ptr_array(list(rscales) + [None] * (4 - len(rscales))), _ptr(col_scale), m, int(bool(with_colsum)), _ptr(dense_b), _ptr(dw),
+         out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    return out if dense_b is None else (out, dw)
+
+
+def adjT_columns_fit(pb, with_colsum: bool, with_dense: bool) -> bool:
+    return 32 * (pb.nw + (1 if with_colsum else 0)) + (128 if with_dense else 0) <= 512
 
 
 def patient_side_supported(pb, n_rows: int, d: int) -> bool:
@@ -925,20 +931,30 @@ class PatientSideFn(Function):
             need_b = any(has_bias[i] and nig[3 + n_w + i] for i in range(n_w))
             want_y = [y_shapes[i] is not None and pb.in_rel[i] is not None and nig[3 + 2 * n_w + i] for i in range(nt)]
             db = _tagged_colsum(dout) if need_b else None          # the producer of dout may have reduced its columns already
+            dw = None
             if any(want_y) and pb.bits_in is not None:
-                # dY_t = (diag(1/deg_t(p)) A_t)^T dout; the bias gradient (column sums of dout) rides along as one more column
-                fuse_b = need_b and db is None and pb.nw + 1 <= 16
-                dy_all = layer_adjT_tc_(dout, pb.bits_in, pb, pb.rscale_in(), None, with_colsum=fuse_b)
+                # ONE pass over dout: dY_t = (diag(1/deg_t(p)) A_t)^T dout, the bias gradient (column sums of dout) as one more
+                # column of ones, and dW_root = dout^T x_p as 128 more columns (when the 512 TMEM columns hold all of it)
+                fuse_b = need_b and db is None and adjT_columns_fit(pb, True, False)
+                fuse_w = need_w and adjT_columns_fit(pb, fuse_b, True)
+                res = layer_adjT_tc_(dout, pb.bits_in, pb, pb.rscale_in(), None, with_colsum=fuse_b, dense_b=x_p if fuse_w else None)
+                dy_all, dw = res if fuse_w else (res, None)
                 if fuse_b:
                     db = dy_all[32 * pb.nw]
                 for i, (off, n) in enumerate(zip(pb.offs, pb.sizes)):
                     if want_y[i]:
                         dys[i] = dy_all[off:off + n]
-            if need_w or (need_b and db is None):
+            if dw is None and need_w:                   # separate weight-gradient launch (and the column sums, if still missing)
                 dw = torch.empty((d, d), dtype=torch.float32, device=dev)
                 db_new = torch.empty(d, dtype=torch.float32, device=dev) if (need_b and db is None) else None
                 linear_bwd_weight_(dout, x_p, dw, db_new)
                 db = db if db_new is None else db_new
+            if need_b and db is None:
+                lib = _lib.load()
+                db = torch.empty(d, dtype=torch.float32, device=dev)
+                ws = workspace(lib.b2g_bn_ws_bytes(d), dev)
+                _run("b2g_col_sums", lib.b2g_col_sums, dout.data_ptr(), m, d, db.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            if dw is not None:
                 for i in range(n_w):
                     if nig[3 + i]:
                         dws[i] = dw

@@ -155,6 +155,13 @@ def test_layer_adjT_tc(m, sizes, density, pkg):
     assert relmax(out3[:32 * pb.nw], out) < 1e-6
     assert relmax(out3[32 * pb.nw], xt.sum(0)) < 2e-5
     assert float(out3[32 * pb.nw + 1:].abs().max()) == 0.0
+    # ... and x^T B for a dense B [m, 128] as 128 more columns (the weight gradient dout^T x_patient), when TMEM holds it all
+    if ops.adjT_columns_fit(pb, True, True):
+        bmat = torch.randn(m, d, generator=gen)
+        out4, dw = ops.layer_adjT_tc_(x.to(dev), pb.bits_in, pb, rs, None, with_colsum=True, dense_b=bmat.to(dev))
+        assert torch.equal(out4, out3), "the adjacency columns must not depend on the dense block"
+        assert relmax(dw, xt.t() @ tf32_trunc(bmat).double()) < 2e-5
+        assert relmax(dw, x.double().t() @ bmat.double()) < 3e-3
 
 
 @pytest.mark.gpu
