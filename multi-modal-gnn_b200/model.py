@@ -509,7 +509,12 @@ class HeteroRGCN(nn.Module):
         if len(self.embeddings) == 0:
             self._init_embeddings(data)
         if not patient_indices.is_cuda or not lab_indices.is_cuda:
-            raise _lib.B2GError("patient_indices / lab_indices must be CUDA tensors")
+            # the reference's EdgeMasker keeps its index tensors on the host (train.py:86,173 -- built before data.to(device)) and
+            # hands them to the model as they are; PyTorch's fancy indexing accepts that, so does the drop-in: the INDEX lists are
+            # staged onto the module's device (this is input staging, not a CPU compute path)
+            dev = self._device()
+            patient_indices = patient_indices.to(dev, non_blocking=True)
+            lab_indices = lab_indices.to(dev, non_blocking=True)
         gi = self._graph_index(data)
         node_types = list(data.node_types)
         streams = self._streams()

@@ -313,3 +313,35 @@ def test_bulk_imputation_hidden_256_matches_oracle(mode):
         assert e1 <= tol and e2 <= tol
     finally:
         ops.set_precision(old)
+
+
+def test_reference_call_sequence_with_host_indices(tf32_mode):
+    """The reference Trainer's call sequence (train.py:210-219, 347-392) against the drop-in on the GPU: model and graph moved to
+    the device, Adam built before the lazy tables exist (N2), and -- as the reference's EdgeMasker does -- the pair indices, the
+    targets and the supervision mask left on the HOST (train.py:86,173).  predict_lab_values stages the index lists itself;
+    loss / backward / optimizer step follow train.py:364-390 with the two device moves INTEGRATION.md section 1 lists."""
+    pkg, G, ops, M, T, MET = _mods()
+    dev = torch.device("cuda:0")
+    g = pkg.synth.make_graph("C1", seed=42)
+    cfg = _cfg(0.2)
+    model = M.build_model(cfg, (g.node_types, g.edge_types), None)
+    model = model.to(dev)                                                   # train.py:210
+    data = pkg.synth.make_graph("C1", seed=42).to(dev)                      # train.py:211
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)  # train.py:219,255-260 (torch's own Adam)
+    assert sum(p.numel() for grp in opt.param_groups for p in grp["params"]) == 483970
+    masker = T.EdgeMasker(g, 0.7, 0.15, 0.15, 0.2, 42)                      # host tensors, like the reference's
+    losses = []
+    for epoch in range(3):
+        model.train()                                                       # train.py:347
+        ei, ev, _, sup = masker.get_masked_data("train", seed=5 + epoch)    # train.py:350 (all on the host)
+        assert not ei.is_cuda and not sup.is_cuda
+        opt.zero_grad()                                                     # train.py:356
+        pred = model.predict_lab_values(data, ei[0], ei[1])                 # train.py:358-362: HOST index tensors
+        assert pred.is_cuda and pred.shape == (ei.shape[1],)
+        p_sup, t_sup = pred[sup.to(dev)], ev[sup].to(dev)                   # train.py:366-368
+        loss = (p_sup - t_sup).abs().mean()                                 # train.py:380 (mae, unweighted branch)
+        loss.backward()                                                     # train.py:389
+        opt.step()                                                          # train.py:390
+        losses.append(float(loss))
+    assert all(l == l and l < 10 for l in losses) and losses[-1] <= losses[0] * 1.05
+    assert model.embeddings["patient"].weight.grad is not None               # N2: tables get gradients but are not optimised

@@ -106,3 +106,29 @@ def test_eval_metrics_restatement_vs_live_reference():
             rows, df = E.per_lab_metrics(pp, t, lab), ev.compute_per_lab_metrics(pp, t, lab, {})
             assert [r["lab_index"] for r in rows] == df["lab_index"].tolist()
             assert [r["num_samples"] for r in rows] == df["num_samples"].tolist()
+
+
+def test_reference_trainer_accepts_the_dropin_model(pkg):
+    """The reference's OWN Trainer (train.py:183-431, unmodified) constructed around the drop-in module (train.py:210-219: model.to,
+    data.to, Adam over model.parameters() BEFORE the lazy tables exist, lab weights from the train split): parameter set,
+    optimizer contents and lab weights are the reference's; without a CUDA device the first forward fails loudly (no CPU
+    path) instead of falling back.  The GPU half of this hand-over -- the reference masker's HOST index tensors fed to
+    predict_lab_values, train.py:350-362 -- is tests/test_gpu_e2e_parity.py::test_reference_call_sequence_with_host_indices."""
+    import importlib
+    M_ref, T_ref = H.load_reference(H.FakeClock())
+    DROP = importlib.import_module("multi-modal-gnn_b200.model")
+    L = importlib.import_module("multi-modal-gnn_b200._lib")
+    g = pkg.synth.make_graph("tiny", seed=3)
+    d = H.to_shim_data(g)
+    cfg = H.make_config(dropout=0.2)
+    model = DROP.build_model(cfg, (d.node_types, d.edge_types), None)          # the drop-in, through the reference's factory signature
+    masker = T_ref.EdgeMasker(d, 0.7, 0.15, 0.15, 0.2, 42)
+    trainer = T_ref.Trainer(model, d, masker, cfg, torch.device("cpu"))
+    n_opt = sum(p.numel() for grp in trainer.optimizer.param_groups for p in grp["params"])
+    assert n_opt == 483970                                                      # KA-1 / note N2: the lazy tables are not in the optimizer
+    ref_model = M_ref.build_model(cfg, (d.node_types, d.edge_types), None)
+    ref_trainer = T_ref.Trainer(ref_model, d, T_ref.EdgeMasker(d, 0.7, 0.15, 0.15, 0.2, 42), cfg, torch.device("cpu"))
+    torch.testing.assert_close(trainer.lab_weights, ref_trainer.lab_weights)
+    assert [k for k, _ in model.named_parameters()] == [k for k, _ in ref_model.named_parameters()]
+    with pytest.raises(L.B2GError, match="no CPU path"):
+        trainer.train_epoch()
