@@ -231,6 +231,14 @@ int b2g_linear_bwd_weight(const float* dy, const float* x, int64_t m, int n, int
 int b2g_linear_fwd_tc_supported(int64_t m, int n, int k);
 int b2g_linear_fwd_tc(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y,
                       int accumulate, void* stream);
+/* The same kernel with an extended epilogue (n <= 128):
+ *   stat_sums != NULL: fp64 {sum y, sum y^2} per column of y -- the statistics of the nn.BatchNorm1d that follows
+ *                      (model.py:93-101) without a pass of its own; ws: b2g_linear_stats_ws_bytes(n);
+ *   inv_norm  != NULL: the rows of y leave the kernel L2-normalised, y /= max(||y||_2, l2_eps) (F.normalize after the last
+ *                      patient-MLP linear, model.py:103-105,232); inv_norm[m] = the reciprocal norms (saved for backward). */
+size_t b2g_linear_stats_ws_bytes(int n);
+int b2g_linear_fwd_tc_ex(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y,
+                         double* stat_sums, void* ws, size_t ws_bytes, float* inv_norm, float l2_eps, void* stream);
 int b2g_transpose(const float* in, int rows, int cols, float* out, void* stream);
 /* dW[N,K] = dy[M,N]^T x[M,K] on tcgen05: both operands MN-major (the reduction index M is the slow one in memory), one
  * fp32 TMEM accumulator per CTA over its whole share of M, per-CTA partials added in fixed order.  Supported when one of

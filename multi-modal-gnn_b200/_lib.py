@@ -111,6 +111,8 @@ _PROTOS = {
     "b2g_linear_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
     "b2g_linear_fwd_tc_supported": (c_int, [c_int64, c_int, c_int]),
     "b2g_linear_fwd_tc": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
+    "b2g_linear_stats_ws_bytes": (c_size_t, [c_int]),
+    "b2g_linear_fwd_tc_ex": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P, c_float, _P]),
     "b2g_transpose": (c_int, [_P, c_int, c_int, _P, _P]),
     "b2g_linear_bwd_weight_tc_supported": (c_int, [c_int64, c_int, c_int]),
     "b2g_linear_bwd_weight_tc_ws_bytes": (c_size_t, [c_int64, c_int, c_int]),

@@ -36,15 +36,23 @@ struct TcParams {
   int tmem_cols;       // 2 * N rounded to a power of two >= 32
   int stages;          // X ring depth: 2 when it fits in shared memory, else 1
   int staged;          // epilogue through the shared-memory staging tile (coalesced stores) when it fits, else direct
+  double* stats;       // null, or per-CTA fp64 column records [grid][2][n] {sum y, sum y^2} (BatchNorm statistics; n <= 128, staged)
+  float* inv_norm;     // null, or [M]: the rows of y are L2-normalised in the epilogue, 1 / max(||row||, eps) is stored here
+  float l2_eps;        //   (F.normalize, model.py:232; needs n <= 128 so that a row lives in one tile, staged, no accumulate)
 };
 
 // dynamic smem layout (1024-byte aligned): W sub-tiles [K/32][N rows x 128 B] | X stages [2][K/32][128 rows x 128 B] |
 // epilogue staging [4 warps][32 rows x 144 B]
+// EXT & 1: BatchNorm column statistics in the epilogue; EXT & 2: row L2 normalisation in the epilogue; EXT = 0: the plain
+// kernel (separate instantiations: the statistics' accumulator registers and unrolled chunk loop cost the plain path 25 %)
+template <int EXT>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_constant__ CUtensorMap map_x,
                                                                const __grid_constant__ CUtensorMap map_w, TcParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_w, bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ double s_stat[4][2][32];
+  __shared__ float s_bias[128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = prm.k / KB;
@@ -56,6 +64,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
   uint8_t* smem_stg = smem_x + (size_t)prm.stages * x_bytes;
   const int64_t n_tiles = (prm.m + TILE_M - 1) / TILE_M;
 
+  if ((EXT & 2) && threadIdx.x < 128) s_bias[threadIdx.x] = (prm.bias && (int)threadIdx.x < prm.n) ? prm.bias[threadIdx.x] : 0.f;
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
     for (int s = 0; s < 2; ++s) {
@@ -123,6 +132,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    float acc_s[4][4], acc_q[4][4];                    // BatchNorm statistics: per-thread fp32 partials, combined in fp64
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc_s[i][j] = acc_q[i][j] = 0.f;
     int it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int s = it & 1;
@@ -133,6 +147,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * prm.n);
       uint8_t* stg = smem_stg + q * STG_WARP;
       const int so = lane & 7, sq = lane >> 3;             // store phase: 16-byte chunk so of row 4j + sq
+      float inv_row = 1.f;                                 // fused F.normalize: this lane's row (TMEM lane = row) is read twice
+      if (EXT & 2) {
+        float ss = 0.f;
+        for (int c0 = 0; c0 < prm.n; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int v = 0; v < 32; ++v) {
+            const float y = __uint_as_float(r[v]) + s_bias[c0 + v];
+            ss = fmaf(y, y, ss);
+          }
+        }
+        inv_row = 1.f / fmaxf(sqrtf(ss), prm.l2_eps);
+        if (row0 + lane < prm.m) prm.inv_norm[row0 + lane] = inv_row;
+      }
       // accumulate mode (out += ...): the previous values of the NEXT 32-column chunk are requested before the current
       // chunk is processed, so that two chunks of loads (16 x 16 B per lane) are in flight -- with one chunk the epilogue
       // warps' memory-level parallelism, not HBM, bounded the kernel at ~2.2 TB/s on HBM-resident outputs
@@ -147,7 +177,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
       };
       const bool acc_staged = prm.accumulate && prm.staged;
       if (acc_staged) load_old(0, oldv);
-      for (int c0 = 0; c0 < prm.n; c0 += 32) {
+#pragma unroll((EXT & 1) ? 8 : 1)
+      for (int ci = 0; ci < 8; ++ci) {                     // (EXT: unrolled, the statistics accumulators are indexed by the chunk)
+        const int c0 = ci * 32;
+        if (c0 >= prm.n) break;
         if (acc_staged && c0 + 32 < prm.n) load_old(c0 + 32, nxtv);
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
@@ -172,13 +205,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
           }
           continue;
         }
+        if (EXT & 2) {                                     // (y + bias) * 1/||row||: the bias is added here, not in the store phase
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
-          *reinterpret_cast<float4*>(stg + lane * STG_ROW + v * 16) =
-              make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<float4*>(stg + lane * STG_ROW + v * 16) =
+                make_float4((__uint_as_float(r[4 * v]) + s_bias[c0 + 4 * v]) * inv_row, (__uint_as_float(r[4 * v + 1]) + s_bias[c0 + 4 * v + 1]) * inv_row,
+                            (__uint_as_float(r[4 * v + 2]) + s_bias[c0 + 4 * v + 2]) * inv_row, (__uint_as_float(r[4 * v + 3]) + s_bias[c0 + 4 * v + 3]) * inv_row);
+        } else {
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<float4*>(stg + lane * STG_ROW + v * 16) =
+                make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+        }
         __syncwarp();
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (prm.bias) b = __ldg(reinterpret_cast<const float4*>(prm.bias + c0) + so);
+        if (prm.bias && !(EXT & 2)) b = __ldg(reinterpret_cast<const float4*>(prm.bias + c0) + so);
+        float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = 4 * j + sq;
@@ -191,6 +233,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
               o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
             }
             *dst = o;
+            if (EXT & 1) {
+              ps[0] += o.x; ps[1] += o.y; ps[2] += o.z; ps[3] += o.w;
+              pq[0] = fmaf(o.x, o.x, pq[0]); pq[1] = fmaf(o.y, o.y, pq[1]); pq[2] = fmaf(o.z, o.z, pq[2]); pq[3] = fmaf(o.w, o.w, pq[3]);
+            }
+          }
+        }
+        if ((EXT & 1) && ci < 4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc_s[ci & 3][e] += ps[e];
+            acc_q[ci & 3][e] += pq[e];
           }
         }
         if (acc_staged) {
@@ -203,11 +256,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[s]);
     }
+    if (EXT & 1) {
+      // column totals of this CTA: lanes with the same column quad hold disjoint rows -> add over lane bits 3,4, then over the
+      // four epilogue warps in warp order through shared memory; one fp64 record per CTA (reduced in CTA order afterwards)
+      const int so = lane & 7, sq = lane >> 3;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        if (ci * 32 < prm.n) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            double a = (double)acc_s[ci][e], b = (double)acc_q[ci][e];
+            a += __shfl_xor_sync(FULL, a, 8);  b += __shfl_xor_sync(FULL, b, 8);
+            a += __shfl_xor_sync(FULL, a, 16); b += __shfl_xor_sync(FULL, b, 16);
+            if (sq == 0) {
+              s_stat[q][0][so * 4 + e] = a;
+              s_stat[q][1][so * 4 + e] = b;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (q == 0) {
+            double* rec = prm.stats + (size_t)blockIdx.x * 2 * prm.n;
+            rec[ci * 32 + lane] = ((s_stat[0][0][lane] + s_stat[1][0][lane]) + s_stat[2][0][lane]) + s_stat[3][0][lane];
+            rec[prm.n + ci * 32 + lane] = ((s_stat[0][1][lane] + s_stat[1][1][lane]) + s_stat[2][1][lane]) + s_stat[3][1][lane];
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(prm.tmem_cols));
+  }
+}
+
+// sums[2n] (fp64) = per-CTA records [n_cta][2][n]: 8 interleaved slices of the records, combined in fixed order
+__global__ void __launch_bounds__(256) k_linear_stats_reduce(const double* __restrict__ rec, int n_cta, int n2, double* __restrict__ sums) {
+  __shared__ double sh[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  double a = 0.0;
+  if (i < n2)
+    for (int c = slice; c < n_cta; c += 8) a += rec[(size_t)c * n2 + i];
+  sh[slice][lane] = a;
+  __syncthreads();
+  if (slice == 0 && i < n2) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) a += sh[k][lane];
+    sums[i] = a;
   }
 }
 
@@ -410,8 +507,28 @@ extern "C" int b2g_linear_fwd_tc_supported(int64_t m, int n, int k) {
   return tc_stages(n, k) > 0 ? 1 : 0;
 }
 
+static int linear_fwd_tc_impl(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y, int accumulate,
+                              double* stat_sums, void* ws, size_t ws_bytes, float* inv_norm, float l2_eps, void* stream_);
+
 extern "C" int b2g_linear_fwd_tc(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y, int accumulate,
                                  void* stream_) {
+  return linear_fwd_tc_impl(x, w, bias, m, n, k, y, accumulate, nullptr, nullptr, 0, nullptr, 0.f, stream_);
+}
+
+extern "C" size_t b2g_linear_stats_ws_bytes(int n) { return ((size_t)sm_count() * 2 * n) * sizeof(double) + 256; }
+
+/* b2g_linear_fwd_tc with an extended epilogue (n <= 128):
+ *   stat_sums != NULL: fp64 {sum y, sum y^2} per column (the statistics of the nn.BatchNorm1d that follows, model.py:93-101),
+ *                      ws: b2g_linear_stats_ws_bytes(n);
+ *   inv_norm  != NULL: the rows of y are L2-normalised, y /= max(||y||_2, l2_eps) (F.normalize after the last MLP linear,
+ *                      model.py:103-105,232), inv_norm[m] receives the reciprocal norms (saved for backward). */
+extern "C" int b2g_linear_fwd_tc_ex(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y,
+                                    double* stat_sums, void* ws, size_t ws_bytes, float* inv_norm, float l2_eps, void* stream_) {
+  return linear_fwd_tc_impl(x, w, bias, m, n, k, y, 0, stat_sums, ws, ws_bytes, inv_norm, l2_eps, stream_);
+}
+
+static int linear_fwd_tc_impl(const float* x, const float* w, const float* bias, int64_t m, int n, int k, float* y, int accumulate,
+                              double* stat_sums, void* ws, size_t ws_bytes, float* inv_norm, float l2_eps, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(x && w && y && b2g_linear_fwd_tc_supported(m, n, k), "linear_fwd_tc: unsupported shape m=%lld n=%d k=%d", (long long)m, n, k);
   B2G_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y) && (!bias || aligned16(bias)), "linear_fwd_tc: pointers must be 16-byte aligned");
@@ -428,16 +545,34 @@ extern "C" int b2g_linear_fwd_tc(const float* x, const float* w, const float* bi
   bool staged = false;
   prm.stages = tc_stages(n, k, &staged);
   prm.staged = staged ? 1 : 0;
+  prm.stats = nullptr; prm.inv_norm = inv_norm; prm.l2_eps = l2_eps;
+  if (stat_sums || inv_norm) {
+    B2G_CHECK_ARG(n <= 128 && staged && !accumulate, "linear_fwd_tc_ex: the extended epilogue needs n <= 128 (n=%d, k=%d)", n, k);
+    if (stat_sums) {
+      if (!ws || ws_bytes < b2g_linear_stats_ws_bytes(n)) {
+        set_error("linear_fwd_tc_ex: workspace too small");
+        return B2G_EWS;
+      }
+      prm.stats = (double*)ws;
+    }
+  }
   const size_t smem = tc_smem(n, k, prm.stages, staged);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    B2G_CUDA(cudaFuncSetAttribute(k_linear_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  B2G_CHECK_ARG(!(stat_sums && inv_norm), "linear_fwd_tc_ex: statistics and row normalisation are separate variants");
+  const int ext = stat_sums ? 1 : (inv_norm ? 2 : 0);
+  static size_t smem_set[3] = {0, 0, 0};
+  auto kern = ext == 1 ? k_linear_tf32<1> : (ext == 2 ? k_linear_tf32<2> : k_linear_tf32<0>);
+  if (smem > smem_set[ext]) {
+    B2G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[ext] = smem;
   }
   int64_t tiles = ceil_div(m, TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  k_linear_tf32<<<grid, TC_THREADS, smem, st>>>(map_x, map_w, prm);
+  kern<<<grid, TC_THREADS, smem, st>>>(map_x, map_w, prm);
   B2G_LAUNCH_CHECK();
+  if (stat_sums) {
+    k_linear_stats_reduce<<<(unsigned)ceil_div(2 * n, 32), 256, 0, st>>>(prm.stats, grid, 2 * n, stat_sums);
+    B2G_LAUNCH_CHECK();
+  }
   return B2G_OK;
 }
 

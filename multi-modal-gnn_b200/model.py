@@ -248,12 +248,17 @@ class HeteroRGCN(nn.Module):
         if "patient" in x:
             pt = self.patient_transform
             shard = sharded == "patient"
-            h = ops.linear(x["patient"], pt[0].weight, pt[0].bias)
+            # the two BatchNorms take their statistics from the preceding linear's epilogue, the row normalisation is the last
+            # linear's epilogue (tf32 mode; the exact-fp32 mode keeps the separate kernels)
+            h = ops.linear(x["patient"], pt[0].weight, pt[0].bias, want_stats=training)
             h = _bn_act_drop(h, pt[1], training, 1, self.dropout, streams, tag + ".drop0", dctx, shard)
-            h = ops.linear(h, pt[4].weight, pt[4].bias)
+            h = ops.linear(h, pt[4].weight, pt[4].bias, want_stats=training)
             h = _bn_act_drop(h, pt[5], training, 1, self.dropout, streams, tag + ".drop1", dctx, shard)
-            h = ops.linear(h, pt[8].weight, pt[8].bias)
-            x["patient"] = ops.L2NormFn.apply(h, 1e-12)
+            if ops.LinearL2NormFn.supported(h, pt[8].weight):
+                x["patient"] = ops.LinearL2NormFn.apply(h, pt[8].weight, pt[8].bias, 1e-12)
+            else:
+                h = ops.linear(h, pt[8].weight, pt[8].bias)
+                x["patient"] = ops.L2NormFn.apply(h, 1e-12)
         return x
 
     def _layer(self, layer: int, x: Dict[str, torch.Tensor], gi: GraphIndex) -> Dict[str, torch.Tensor]:

@@ -299,11 +299,23 @@ class LinearFn(Function):
     """y = x W^T + b   (nn.Linear; model.py:93-103,373-386 and SAGEConv.lin_l / lin_r)."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, want_stats=False):
         x, w = _f32(x, "x"), _f32(w, "weight")
         b = None if b is None else _f32(b, "bias")
         y = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
-        linear_fwd_(x, w, b, y)
+        lib = _lib.load()
+        m, k = x.shape
+        n = w.shape[0]
+        if want_stats and n <= 128 and _use_tc(lib, m, n, k) and (b is None or b.data_ptr() % 16 == 0):
+            # the BatchNorm that follows (model.py:93-101) gets its column statistics from this launch's epilogue
+            sums = torch.empty(2 * n, dtype=torch.float64, device=x.device)
+            ws = workspace(lib.b2g_linear_stats_ws_bytes(n), x.device)
+            cost(4 * (m * k + n * k + m * n), 2 * m * n * k)
+            _run("b2g_linear_fwd_tc", lib.b2g_linear_fwd_tc_ex, x.data_ptr(), w.data_ptr(), _ptr(b), m, n, k, y.data_ptr(), sums.data_ptr(),
+                 ws.data_ptr(), ws.numel(), None, 0.0, _stream())
+            _tag_bnsums(y, sums)
+        else:
+            linear_fwd_(x, w, b, y)
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         ctx.set_materialize_grads(False)
@@ -313,7 +325,7 @@ class LinearFn(Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         if dy is None:
-            return None, None, None
+            return None, None, None, None
         dy = _f32(dy, "grad")
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
@@ -324,11 +336,59 @@ class LinearFn(Function):
             dw = torch.empty_like(w)
             db = torch.empty(w.shape[0], dtype=torch.float32, device=w.device) if need_b else None
             linear_bwd_weight_(dy, x, dw, db)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
-def linear(x, w, b=None):
-    return LinearFn.apply(x, w, b)
+def linear(x, w, b=None, want_stats=False):
+    return LinearFn.apply(x, w, b, want_stats)
+
+
+class LinearL2NormFn(Function):
+    """F.normalize(x W^T + b, p=2, dim=1, eps)  -- the last patient-MLP linear and the row normalisation that follows it
+    (model.py:101-105,232) in ONE launch: the tcgen05 kernel's epilogue holds whole rows (N = 128), computes their norms from
+    the TMEM accumulator and stores the normalised rows; the un-normalised product never goes to HBM.  Backward = the
+    normalisation's backward kernel followed by the linear's."""
+
+    @staticmethod
+    def supported(x, w) -> bool:
+        lib = _lib.load()
+        return w.shape[0] <= 128 and _use_tc(lib, x.shape[0], w.shape[0], x.shape[1])
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        lib = _lib.load()
+        x, w = _f32(x, "x"), _f32(w, "weight")
+        b = None if b is None else _f32(b, "bias")
+        m, k = x.shape
+        n = w.shape[0]
+        y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+        inv = torch.empty(m, dtype=torch.float32, device=x.device)
+        cost(4 * (m * k + n * k + m * n), 2 * m * n * k)
+        _run("b2g_linear_fwd_tc", lib.b2g_linear_fwd_tc_ex, x.data_ptr(), w.data_ptr(), _ptr(b), m, n, k, y.data_ptr(), None, None, 0,
+             inv.data_ptr(), float(eps), _stream())
+        ctx.save_for_backward(x, w, y, inv)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, w, y, inv = ctx.saved_tensors
+        dy = _f32(dy, "grad")
+        m, n = y.shape
+        g = torch.empty_like(y)
+        cost(12 * m * n)
+        _run("b2g_l2norm_bwd", lib.b2g_l2norm_bwd, y.data_ptr(), dy.data_ptr(), inv.data_ptr(), m, n, g.data_ptr(), _stream())
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            linear_bwd_input_(g, w, dx)
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or need_b:
+            dw = torch.empty_like(w)
+            db = torch.empty(w.shape[0], dtype=torch.float32, device=w.device) if need_b else None
+            linear_bwd_weight_(g, x, dw, db)
+        return dx, dw, db, None
 
 
 class GroupedLinearFn(Function):

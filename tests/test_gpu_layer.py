@@ -253,7 +253,8 @@ def test_batchnorm_statistics_come_from_the_layer_epilogue(pkg):
                 ops.PROFILE = None
                 M.HeteroRGCN._layer_fused = saved
             res[fused] = (out, {k: v.clone() for k, v in model.state_dict().items() if "running" in k}, names)
-        assert res[True][2].count("b2g_bn_finalize_sums") == 2, "both GNN layers' patient BatchNorms should use the epilogue statistics"
+        # 2 patient-MLP BatchNorms (statistics from k_linear_tf32's epilogue, both paths) + 2 GNN-layer patient BatchNorms (fused only)
+        assert res[True][2].count("b2g_bn_finalize_sums") == 4 and res[False][2].count("b2g_bn_finalize_sums") == 2
         assert res[True][2].count("b2g_bn_stats") == res[False][2].count("b2g_bn_stats") - 2
         for nt in res[True][0]:
             assert relmax(res[True][0][nt], res[False][0][nt]) < 5e-3, nt
@@ -261,3 +262,47 @@ def test_batchnorm_statistics_come_from_the_layer_epilogue(pkg):
             assert relmax(res[True][1][k], res[False][1][k]) < 2e-3, k
     finally:
         ops.set_precision(old)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n,k", [(512, 128, 128), (4099, 128, 128), (70001, 128, 128), (5000, 64, 128), (3000, 128, 64)])
+def test_linear_epilogue_statistics_and_l2norm(m, n, k, pkg):
+    """k_linear_tf32's extended epilogue (b2g_linear_fwd_tc_ex): BatchNorm column statistics of y = x W^T + b, and
+    F.normalize(y) with the reciprocal norms (model.py:93-105,232), against torch in float64 on TF32-truncated operands."""
+    G, ops, _, _, L = _mods()
+    lib = L.load()
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(m + n)
+    x = torch.randn(m, k, generator=gen)
+    w = torch.randn(n, k, generator=gen) / k ** 0.5
+    b = torch.randn(n, generator=gen)
+    ref = tf32_trunc(x).double() @ tf32_trunc(w).double().t() + b.double()
+    xd, wd, bd = x.to(dev), w.to(dev), b.to(dev)
+    y = torch.empty(m, n, device=dev)
+    sums = torch.zeros(2 * n, dtype=torch.float64, device=dev)
+    ws = torch.empty(lib.b2g_linear_stats_ws_bytes(n), dtype=torch.uint8, device=dev)
+    L.check(lib.b2g_linear_fwd_tc_ex(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), m, n, k, y.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     None, 0.0, None))
+    torch.cuda.synchronize()
+    assert relmax(y, ref) < 2e-5
+    y64 = y.double().cpu()
+    torch.testing.assert_close(sums[:n].cpu(), y64.sum(0), rtol=2e-6, atol=2e-6 * m)
+    torch.testing.assert_close(sums[n:].cpu(), (y64 * y64).sum(0), rtol=2e-6, atol=2e-6 * m)
+    # fused row normalisation
+    y2 = torch.empty(m, n, device=dev)
+    inv = torch.empty(m, device=dev)
+    L.check(lib.b2g_linear_fwd_tc_ex(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), m, n, k, y2.data_ptr(), None, None, 0, inv.data_ptr(), 1e-12, None))
+    torch.cuda.synchronize()
+    nrm = ref.norm(dim=1).clamp_min(1e-12)
+    assert relmax(y2, ref / nrm[:, None]) < 2e-5
+    assert relmax(inv, 1.0 / nrm) < 2e-5
+    # autograd wrapper == separate linear + normalize
+    ops.set_precision("tf32")
+    xa, wa, ba = xd.clone().requires_grad_(True), wd.clone().requires_grad_(True), bd.clone().requires_grad_(True)
+    xb, wb, bb = xd.clone().requires_grad_(True), wd.clone().requires_grad_(True), bd.clone().requires_grad_(True)
+    go = torch.randn(m, n, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    if ops.LinearL2NormFn.supported(xa, wa):
+        ops.LinearL2NormFn.apply(xa, wa, ba, 1e-12).backward(go)
+        ops.L2NormFn.apply(ops.linear(xb, wb, bb), 1e-12).backward(go)
+        for a_, b_ in ((xa, xb), (wa, wb), (ba, bb)):
+            assert relmax(a_.grad, b_.grad) < 5e-4          # (the two forward results differ in the last bits: fused vs separate normalisation)
