@@ -152,16 +152,25 @@ int b2g_adj_bits_build(const int32_t* rowptr, const int32_t* col, int64_t n_rows
 int b2g_layer_cat_weights(const float* const* h_ws, int n_w, int w_transposed, const float* const* h_biases, int n_b,
                           float* bias_out, int n, int kx, const float* const* h_tabs, const float* const* h_scales,
                           const int* h_rows, const int* h_offs, int n_rel, int ktot, float* out, void* stream);
+/* Half mode of the adjacency columns (optional; what the default tf32 precision mode uses): for every row j of wcat (= output
+ * column j of the layer), whalf[j, :] = fp16_rn(wcat[j, kx:] * 2^e_j), zero-padded to 64 * ceil(nw / 2) columns, with the power
+ * of two that puts the row's largest |value| into [2^13, 2^14); wcat[j, :kx] *= 2^e_j in place (exact); unscale[j] = 2^-e_j.
+ * The adjacency entries are {0, 1/deg} -- fp16 holds them with 11 significant bits, rounded to nearest (TF32 as the tensor core
+ * reads it: 11 bits, truncated) -- so b2g_layer_fwd_tc can run the adjacency part of the reduction with kind::f16 MMAs on
+ * operand tiles half as large as the TF32 ones (shared-memory bandwidth, not HBM, bounds that kernel). */
+int b2g_layer_cat_half(float* wcat, int n, int kx, int ktot, uint16_t* whalf, float* unscale, void* stream);
 /* y[m, n] = x[m, kx] . wcat[:, :kx]^T + (diag(rscale) A)[m, 32 nw] . wcat[:, kx:]^T + bias      (tcgen05, TF32 operands)
  *   forward : x = x_patient, wcat = [sum_r W_r,root | Y_lab | Y_dx | Y_med] with Y_r = x_r W_l,r^T, rscale_r = 1/deg_r(patient)
  *   backward: x = dout_patient, wcat = [W_root^T | dagg_r / deg_r(type)], rscale = NULL  ->  dx_patient
  * K-chunk pipelined: TMA (x chunk, wcat chunk) + expander warps (bits -> swizzled TF32 A chunk) -> tcgen05.mma -> TMEM,
  * double-buffered accumulator, epilogue TMEM -> staging -> coalesced stores.  stat_sums (optional, n <= 128): fp64
  * {sum, sum of squares} per column of y (BatchNorm statistics of the layer output, model.py:259-261) produced by the
- * epilogue; ws: b2g_layer_stats_ws_bytes(n) (only when stat_sums is given). */
+ * epilogue; ws: b2g_layer_stats_ws_bytes(n) (only when stat_sums is given).
+ * whalf / unscale (both or neither): the outputs of b2g_layer_cat_half -- the adjacency part then runs in half mode
+ * (x part: kind::tf32, adjacency part: kind::f16 into the same fp32 TMEM accumulator; y = acc * unscale + bias). */
 int b2g_layer_fwd_tc_supported(int64_t m, int n, int kx, int nw);
 size_t b2g_layer_stats_ws_bytes(int n);
-int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* bias, const uint32_t* bits,
+int b2g_layer_fwd_tc(const float* x, const float* wcat, const uint16_t* whalf, const float* unscale, const float* bias, const uint32_t* bits,
                      const b2g_bit_layout_t* h_layout, const float* const* h_rscale, int64_t m, int n, int kx, float* y,
                      double* stat_sums, void* ws, size_t ws_bytes, void* stream);
 /* out[32 nw, 128] = col_scale[:, None] * (diag(rscale) A)^T . x[m, 128]       (tcgen05, MN-major TF32 operands)

@@ -174,7 +174,8 @@ _PROTOS = {
                                       c_int, c_int, _P, _P]),
     "b2g_layer_fwd_tc_supported": (c_int, [c_int64, c_int, c_int, c_int]),
     "b2g_layer_stats_ws_bytes": (c_size_t, [c_int]),
-    "b2g_layer_fwd_tc": (c_int, [_P, _P, _P, _P, ctypes.POINTER(BitLayoutT), ctypes.POINTER(c_void_p), c_int64, c_int, c_int, _P, _P, _P,
+    "b2g_layer_cat_half": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
+    "b2g_layer_fwd_tc": (c_int, [_P, _P, _P, _P, _P, _P, ctypes.POINTER(BitLayoutT), ctypes.POINTER(c_void_p), c_int64, c_int, c_int, _P, _P, _P,
                                  c_size_t, _P]),
     "b2g_layer_adjT_tc_supported": (c_int, [c_int64, c_int, c_int]),
     "b2g_layer_adjT_tc_ws_bytes": (c_size_t, [c_int]),

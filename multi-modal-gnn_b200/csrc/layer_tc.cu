@@ -17,6 +17,7 @@
 // HBM traffic per patient row: forward 512 B (x_p) + 512 B (out_p) + bits; the reduction operands (W_root | Y, 128 x K fp32)
 // stream from L2 one 32-column chunk at a time next to the matching A chunk.
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace {
@@ -27,8 +28,7 @@ constexpr int LY_MAXREL = 4;
 constexpr int LY_THREADS = 384;                  // warps: 0 TMA, 1 MMA, 4-7 epilogue, 2-3 and 8-11 expanders (2 also owns TMEM)
 constexpr int LY_MAX_STAGES = 6;
 constexpr int A_CHUNK = TILE_M * KB * 4;         // [128 rows x 128 B] = 16 KB
-constexpr int STG_ROW = 128 + 16;                // epilogue staging row: 32 floats + 16 B pad (conflict-free 16-byte accesses)
-constexpr int STG_WARP = 32 * STG_ROW;
+constexpr int STG_WARP = 32 * 128;               // epilogue staging tile of one warp: 32 rows x 32 floats, TMA SWIZZLE_128B layout
 constexpr int STG_BYTES = 4 * STG_WARP;
 
 // description of the bit layout: word w of a row holds columns [32 w, 32 w + 32) of the concatenated type axis.  Bits
@@ -53,8 +53,11 @@ struct LayerParams {
   int kx;                              // dense reduction columns (x), multiple of 32 (may be 0)
   int tmem_cols;
   int stages;
+  int half_adj;                        // 1: adjacency chunks are 64 columns of fp16 {0 | s} fed to kind::f16 (B rows from map_h), see below
+  const float* unscale;                // half_adj: y = acc * unscale[col] + bias (the B rows carry a power-of-two scale per output column)
   long long* dbg_out;                  // diagnosis only (dbg & 8): per-role wait cycles of CTA 0
-  int dbg;                             // diagnosis only (B2G_LAYER_DBG): 1 = skip the bit expansion, 2 = skip the B loads, 4 = skip x loads
+  int dbg;                             // diagnosis only (B2G_LAYER_DBG): 1 = skip the bit expansion, 2 = skip the B loads, 4 = skip x loads,
+                                       // 16 = half mode with kind::tf32 MMAs on the adjacency chunks (wrong results: timing of the kind change)
 };
 
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
@@ -80,30 +83,68 @@ __device__ __forceinline__ uint4 expand4(uint32_t word, int b0, uint32_t sbits) 
   return v;
 }
 
-// dynamic smem (1024-byte aligned): stages [A chunk 16 KB | B chunk n x 128 B] | epilogue staging [4 warps][32 rows x 144 B]
+// half mode: 32 adjacency bits -> 32 fp16 entries {0 | s} = four 16-byte pieces (piece j = bits 8j .. 8j+7), pure ALU.
+// v_k = w << (7 - k) carries bit 8b + k of w in the sign position of its byte b; PRMT with the replicate-sign flag (0x8) in a
+// selector nibble turns that sign into a whole byte, so one PRMT of (v_2q, v_2q+1) makes the two 16-bit masks of bits
+// 8j + 2q, 8j + 2q + 1.  7 shifts + 16 PRMT + 16 AND per word, no shared-memory look-up: the expander's stores never wait
+// for a load (the look-up-table form serialised LDS -> STS per piece, because the table could alias the stores).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// TF32 form: entries 4j .. 4j+3 of the word as 32-bit {0 | s}: one PRMT (sign of one byte replicated into all four) + AND each
+__device__ __forceinline__ void shifts8(uint32_t w, uint32_t (&v)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = w << (7 - k);
+}
+__device__ __forceinline__ uint4 expand4_t(const uint32_t (&v)[8], int j, uint32_t s) {
+  const uint32_t sel = (0x8u | (uint32_t)(j >> 1)) * 0x1111u;
+  const int k0 = (j & 1) * 4;
+  return make_uint4(prmt(v[k0], 0u, sel) & s, prmt(v[k0 + 1], 0u, sel) & s, prmt(v[k0 + 2], 0u, sel) & s, prmt(v[k0 + 3], 0u, sel) & s);
+}
+__device__ __forceinline__ void expand_word_h(uint32_t w, uint32_t s2, uint4 (&out)[4]) {
+  uint32_t v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = w << (7 - k);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t sel = (0x8u | j) * 0x11u | (0xCu | j) * 0x1100u;
+    out[j] = make_uint4(prmt(v[0], v[1], sel) & s2, prmt(v[2], v[3], sel) & s2, prmt(v[4], v[5], sel) & s2, prmt(v[6], v[7], sel) & s2);
+  }
+}
+
+// dynamic smem (1024-byte aligned): stages [A chunk 16 KB | B chunk n x 128 B] | epilogue staging [4 warps][32 rows x 128 B] |
+// bias[256], unscale[256] | 2 slots [128 x nw words | 4 x 128 row scales]
 __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_constant__ CUtensorMap map_x,
                                                               const __grid_constant__ CUtensorMap map_w,
+                                                              const __grid_constant__ CUtensorMap map_h,
+                                                              const __grid_constant__ CUtensorMap map_y,
                                                               const __grid_constant__ LayerParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[LY_MAX_STAGES], bar_empty[LY_MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ __align__(8) uint64_t bar_full[LY_MAX_STAGES], bar_empty[LY_MAX_STAGES], bar_tfull[2], bar_tempty[2], bar_bits[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ double s_stat[4][2][32];
-  __shared__ uint4 s_lut[16];                          // nibble -> four {0 | ~0} masks (a byte table + PRMT costs more ALU than it saves)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < 16)
-    s_lut[threadIdx.x] = make_uint4((threadIdx.x & 1) ? ~0u : 0u, (threadIdx.x & 2) ? ~0u : 0u, (threadIdx.x & 4) ? ~0u : 0u, (threadIdx.x & 8) ? ~0u : 0u);
   const int nxc = prm.kx / KB;                         // chunks fed by TMA from x
   const int nw = prm.bl.nw;
-  const int nc = nxc + nw;                             // chunks per tile
+  const bool half_adj = prm.half_adj != 0;
+  const int nc = nxc + (half_adj ? (nw + 1) / 2 : nw); // chunks per tile (a half-mode adjacency chunk covers two words = 64 columns)
   const uint32_t b_bytes = (uint32_t)prm.n * KB * 4;
   const uint32_t stage_bytes = A_CHUNK + b_bytes;
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   uint8_t* smem_stg = base + (size_t)prm.stages * stage_bytes;
+  uint8_t* smem_bu = smem_stg + STG_BYTES;
+  uint8_t* smem_bits = smem_bu + 2048;                 // half mode: 2 slots of [128 x nw words | LY_MAXREL x 128 row scales]
+  for (int i = threadIdx.x; i < 256; i += LY_THREADS) {
+    reinterpret_cast<float*>(smem_bu)[i] = (prm.bias && i < prm.n) ? __ldg(prm.bias + i) : 0.f;
+    reinterpret_cast<float*>(smem_bu)[256 + i] = (prm.unscale && i < prm.n) ? __ldg(prm.unscale + i) : 1.f;
+  }
+  const uint32_t bits_slot = (uint32_t)TILE_M * nw * 4 + LY_MAXREL * TILE_M * 4;
   const int64_t n_tiles = (prm.m + TILE_M - 1) / TILE_M;
   const int nst = prm.stages;
   const bool tm = (prm.dbg & 8) && blockIdx.x == 0;
-  long long w0 = 0, w1 = 0;
+  long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
   const long long t_begin = clock64();
 
   if (threadIdx.x == 0) {
@@ -114,6 +155,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
       mbar_init(&bar_tempty[s], 4);
+      mbar_init(&bar_bits[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -131,13 +173,18 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 1;                                 // parity to wait for on bar_empty (the first pass over the ring is free)
-      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        for (int c = 0; c < nc; ++c) {
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        for (int cp = 0; cp < nc; ++cp) {
+          const int c = cp;
           mbar_wait_t(&bar_empty[s], ph, w0, tm);
           uint8_t* st = base + (size_t)s * stage_bytes;
           const bool ldb = !(prm.dbg & 2), ldx = c < nxc && !(prm.dbg & 4);
           mbar_expect_tx(&bar_full[s], (ldb ? b_bytes : 0u) + (ldx ? (uint32_t)A_CHUNK : 0u));
-          if (ldb) tma_load_2d(st + A_CHUNK, &map_w, &bar_full[s], c * KB, 0);
+          if (ldb) {
+            if (half_adj && c >= nxc) tma_load_2d(st + A_CHUNK, &map_h, &bar_full[s], (c - nxc) * 64, 0);
+            else tma_load_2d(st + A_CHUNK, &map_w, &bar_full[s], c * KB, 0);
+          }
           if (ldx) tma_load_2d(st, &map_x, &bar_full[s], c * KB, (int)(t * TILE_M));
           if (++s == nst) { s = 0; ph ^= 1; }
         }
@@ -147,7 +194,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
     // ===== MMA issuer: ONE thread runs the whole loop; stage / phase counters are incremental and the shared-memory
     // descriptors are formed by adding the stage offset to a descriptor with a zero start address =====
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(prm.n);
+      const uint32_t idesc = make_idesc(prm.n), idesc_h = make_idesc_f16(prm.n);
       const uint64_t dhi = make_desc(0);
       const uint32_t base16 = smem_u32(base) >> 4, st16 = stage_bytes >> 4, a16 = A_CHUNK >> 4;
       int s = 0, it = 0;
@@ -157,15 +204,22 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
         mbar_wait_t(&bar_tempty[a], ((it >> 1) & 1) ^ 1, w1, tm);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * prm.n);
-        for (int c = 0; c < nc; ++c) {
-          mbar_wait_t(&bar_full[s], ph, w0, tm);
+        for (int cp = 0; cp < nc; ++cp) {
+          const int c = cp;
+          if (c < nxc) mbar_wait_t(&bar_full[s], ph, w0, tm);
+          else mbar_wait_t(&bar_full[s], ph, w2, tm);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = dhi + (base16 + (uint32_t)s * st16);
           const uint64_t db = da + a16;
+          if (half_adj && c >= nxc && !(prm.dbg & 16)) {
 #pragma unroll
-          for (int k8 = 0; k8 < KB / 8; ++k8) umma_tf32(d_tmem, da + 2 * k8, db + 2 * k8, idesc, (c | k8) != 0);
+            for (int k16 = 0; k16 < 4; ++k16) umma_f16(d_tmem, da + 2 * k16, db + 2 * k16, idesc_h, (cp | k16) != 0);
+          } else {
+#pragma unroll
+            for (int k8 = 0; k8 < KB / 8; ++k8) umma_tf32(d_tmem, da + 2 * k8, db + 2 * k8, idesc, (cp | k8) != 0);
+          }
           umma_commit(&bar_empty[s]);
-          if (c == nc - 1) umma_commit(&bar_tfull[a]);
+          if (cp == nc - 1) umma_commit(&bar_tfull[a]);
           if (++s == nst) { s = 0; ph ^= 1; }
         }
       }
@@ -174,13 +228,107 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
     // ===== expanders: adjacency bits -> TF32 A chunks (K-major SWIZZLE_128B: 16-byte chunk j of row r at j ^ (r & 7)) =====
     // Expander warp e is bound to pipeline stage e: it handles every chunk g = e (mod stages) -- all 128 rows of the chunk,
     // 4 rows per lane -- so up to `stages` chunks are being expanded at the same time, and it sees every phase of its stage's
-    // barriers in order (a warp that skipped phases could not use parity waits).  A nibble of the word indexes a 16-entry
-    // look-up table of four {0 | ~0} masks (one LDS.128 instead of ~12 ALU instructions per 4 entries).
+    // barriers in order (a warp that skipped phases could not use parity waits).  The entries come from PRMT sign
+    // replication (expand4_t / expand_word_h): pure ALU, so the stores never wait for a load.
     // For an x chunk there is nothing to expand: the warp only contributes the stage's second arrival.
     const int e = warp >= 8 ? warp - 6 : warp - 2;     // 0..5
     if (e < nst) {
       const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       const uint32_t total = (uint32_t)(my_tiles * nc);
+      if (half_adj) {
+        // half mode: chunk k covers words 2k, 2k+1 of the row = 64 columns of fp16 {0 | fp16(scale)}: the 16-byte piece j of the
+        // row (8 columns = one byte of the word pair) comes from expand_word_h (PRMT sign replication) ANDed with the row scale
+        // replicated in both halves of a register; half the shared-memory stores and half the MMA operand reads of the TF32 form.
+        auto h2 = [](float f) -> uint32_t {
+          const __half2 v = __float2half2_rn(f);
+          return *reinterpret_cast<const uint32_t*>(&v);
+        };
+        // The words and row scales of a whole tile (128 x nw words, contiguous in global memory, + 128 floats per relation) are
+        // brought into a two-slot shared-memory buffer by bulk copies that an epilogue thread issues one tile ahead
+        // (bar_bits[slot]); per-lane global loads here (24 per chunk, one 32-byte sector each) cost 0.08 ms per launch.
+        // A partial last tile is read with plain loads instead (the bulk copy would run past the arrays).
+        int cp = e % nc, it = e / nc;                    // position in the tile and tile counter of this warp's next chunk
+        int64_t t = blockIdx.x + (int64_t)it * gridDim.x;
+        uint32_t ph = 1;
+        for (uint32_t g = (uint32_t)e; g < total; g += (uint32_t)nst, ph ^= 1) {
+          const int c = cp;
+          mbar_wait_t(&bar_empty[e], ph, w0, tm);
+          if (c >= nxc && !(prm.dbg & 1)) {
+            const int k0 = 2 * (c - nxc);
+            uint32_t wc[4][2], sc[4][4];
+            if ((t + 1) * TILE_M <= prm.m) {
+              mbar_wait_t(&bar_bits[it & 1], (uint32_t)(it >> 1) & 1u, w1, tm);
+              const uint32_t* sbits = reinterpret_cast<const uint32_t*>(smem_bits + (size_t)(it & 1) * bits_slot);
+              const float* sscale = reinterpret_cast<const float*>(smem_bits + (size_t)(it & 1) * bits_slot + (size_t)TILE_M * nw * 4);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int k = k0 + h;
+                const bool kv = k < nw;
+                const int ra = kv ? prm.bl.rel_a[k] : 0, rb = kv ? prm.bl.rel_b[k] : 0;
+                const bool has_a = kv && prm.rscale[ra] != nullptr, has_b = kv && prm.rscale[rb] != nullptr;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int r = i * 32 + lane;
+                  wc[i][h] = kv ? sbits[r * nw + k] : 0u;
+                  sc[i][2 * h] = has_a ? h2(sscale[ra * TILE_M + r]) : 0x3C003C00u;
+                  sc[i][2 * h + 1] = has_b ? h2(sscale[rb * TILE_M + r]) : 0x3C003C00u;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int k = k0 + h;
+                const bool kv = k < nw;
+                const float* ra = kv ? prm.rscale[prm.bl.rel_a[k]] : nullptr;
+                const float* rb = kv ? prm.rscale[prm.bl.rel_b[k]] : nullptr;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int64_t row = t * TILE_M + i * 32 + lane;
+                  const bool live = kv && row < prm.m;
+                  wc[i][h] = live ? __ldg(prm.bits + (size_t)row * nw + k) : 0u;
+                  sc[i][2 * h] = (live && ra) ? h2(__ldg(ra + row)) : 0x3C003C00u;
+                  sc[i][2 * h + 1] = (live && rb) ? h2(__ldg(rb + row)) : 0x3C003C00u;
+                }
+              }
+            }
+            uint8_t* abase = base + (size_t)e * stage_bytes;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int split = (k0 + h < nw) ? prm.bl.split[k0 + h] : 32;
+              if (split >= 32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int r = i * 32 + lane;
+                  uint8_t* arow = abase + r * 128;
+                  uint4 pc[4];
+                  expand_word_h(wc[i][h], sc[i][2 * h], pc);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(arow + (((4 * h + j) ^ (r & 7)) << 4)) = pc[j];
+                }
+              } else {
+                const uint32_t msk = (1u << split) - 1u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int r = i * 32 + lane;
+                  uint8_t* arow = abase + r * 128;
+                  uint4 pa[4], pb[4];
+                  expand_word_h(wc[i][h] & msk, sc[i][2 * h], pa);
+                  expand_word_h(wc[i][h] & ~msk, sc[i][2 * h + 1], pb);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(arow + (((4 * h + j) ^ (r & 7)) << 4)) =
+                        make_uint4(pa[j].x | pb[j].x, pa[j].y | pb[j].y, pa[j].z | pb[j].z, pa[j].w | pb[j].w);
+                }
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_full[e]);
+          cp += nst;
+          while (cp >= nc) { cp -= nc; t += gridDim.x; ++it; }
+        }
+      } else {
       uint32_t wn[4], san[4], sbn[4];
       int cn = e % nc;                                 // chunk-in-tile and tile counter of the chunk being prefetched
       int64_t tn = blockIdx.x + (int64_t)(e / nc) * gridDim.x;
@@ -192,7 +340,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int64_t row = tn * TILE_M + i * 32 + lane;
-          const bool live = row < prm.m;
+          const bool live = row < prm.m && !(prm.dbg & 64);
           wn[i] = live ? __ldg(prm.bits + (size_t)row * nw + k) : 0u;
           san[i] = (live && ra) ? __float_as_uint(__ldg(ra + row)) : 0x3f800000u;
           sbn[i] = (live && rb) ? __float_as_uint(__ldg(rb + row)) : 0x3f800000u;
@@ -218,11 +366,10 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
             for (int i = 0; i < 4; ++i) {
               const int r = i * 32 + lane;
               uint8_t* arow = abase + r * 128;
+              uint32_t v[8];
+              shifts8(wc[i], v);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint4 m4 = s_lut[(wc[i] >> (4 * j)) & 15u];
-                *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) = make_uint4(m4.x & sac[i], m4.y & sac[i], m4.z & sac[i], m4.w & sac[i]);
-              }
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) = expand4_t(v, j, sac[i]);
             }
           } else {
             const uint32_t msk = (1u << split) - 1u;
@@ -230,13 +377,13 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
             for (int i = 0; i < 4; ++i) {
               const int r = i * 32 + lane;
               uint8_t* arow = abase + r * 128;
-              const uint32_t lo = wc[i] & msk, hi = wc[i] & ~msk;
+              uint32_t va[8], vb[8];
+              shifts8(wc[i] & msk, va);
+              shifts8(wc[i] & ~msk, vb);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const uint4 ma = s_lut[(lo >> (4 * j)) & 15u], mb = s_lut[(hi >> (4 * j)) & 15u];
-                *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) =
-                    make_uint4((ma.x & sac[i]) | (mb.x & sbc[i]), (ma.y & sac[i]) | (mb.y & sbc[i]), (ma.z & sac[i]) | (mb.z & sbc[i]),
-                               (ma.w & sac[i]) | (mb.w & sbc[i]));
+                const uint4 pa = expand4_t(va, j, sac[i]), pb = expand4_t(vb, j, sbc[i]);
+                *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) = make_uint4(pa.x | pb.x, pa.y | pb.y, pa.z | pb.z, pa.w | pb.w);
               }
             }
           }
@@ -245,90 +392,128 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_full[e]);
       }
+      }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> staging tile -> coalesced 16-byte stores (+ bias, + BatchNorm column sums) =====
+    // ===== epilogue: TMEM -> registers (lane = row, 32 consecutive columns) -> y = acc * unscale + bias -> the warp's 4 KB
+    // staging tile in the TMA's SWIZZLE_128B layout (conflict-free 16-byte stores) -> ONE bulk tensor store per 32 x 32 block
+    // (cp.async.bulk.tensor: rows beyond m are clipped by the tensor map).  The stores leave the SM without LDS / STG work;
+    // the BatchNorm column sums are read back from the staging tile, lane = column. =====
     const int q = warp & 3;
-    const int so = lane & 7, sq = lane >> 3;
-    double acc_s[4][4], acc_q[4][4];                   // [32-column chunk][column of this lane's quad]: sum, sum of squares
-#pragma unroll                                         // (statistics are offered for n <= 128 only: register budget)
-    for (int i = 0; i < 4; ++i)
+    uint8_t* stg = smem_stg + q * STG_WARP;
+    const float* s_bias = reinterpret_cast<const float*>(smem_bu);
+    const float* s_us = s_bias + 256;
+    double acc_s[4], acc_q[4];                         // column (32 ci + lane) of this warp's rows: sum, sum of squares
+#pragma unroll                                         // (statistics are offered for n <= 128 only)
+    for (int i = 0; i < 4; ++i) acc_s[i] = acc_q[i] = 0.0;
+    // half mode: thread (warp 4, lane 0) feeds the expanders' bits / row-scale slots: tiles 0 and 1 up front, tile it + 2 into
+    // slot it & 1 as soon as tile it is complete (its MMAs have committed, so every expander is done reading the slot)
+    auto issue_bits = [&](int64_t t, int slot) {
+      if (t >= n_tiles || (t + 1) * TILE_M > prm.m) return;
+      uint8_t* dst = smem_bits + (size_t)slot * bits_slot;
+      const uint32_t wbytes = (uint32_t)TILE_M * nw * 4;
+      uint32_t total = wbytes;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc_s[i][j] = acc_q[i][j] = 0.0;
+      for (int r = 0; r < LY_MAXREL; ++r) total += prm.rscale[r] ? TILE_M * 4u : 0u;
+      mbar_expect_tx(&bar_bits[slot], total);
+      bulk_load(dst, prm.bits + (size_t)t * TILE_M * nw, wbytes, &bar_bits[slot]);
+#pragma unroll
+      for (int r = 0; r < LY_MAXREL; ++r)
+        if (prm.rscale[r]) bulk_load(dst + wbytes + r * TILE_M * 4, prm.rscale[r] + t * TILE_M, TILE_M * 4u, &bar_bits[slot]);
+    };
+    const bool feeder = half_adj && warp == 4 && lane == 0;
+    if (feeder) {
+      issue_bits(blockIdx.x, 0);
+      issue_bits((int64_t)blockIdx.x + gridDim.x, 1);
+    }
     int it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       mbar_wait_t(&bar_tfull[s], ph, w0, tm);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (feeder) issue_bits(t + 2 * (int64_t)gridDim.x, s);
       const int64_t row0 = t * TILE_M + q * 32;
+      const bool live = row0 + lane < prm.m;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * prm.n);
-      uint8_t* stg = smem_stg + q * STG_WARP;
+      uint32_t rg[32];
+      tmem_ld32(taddr, rg);                            // (the load of block ci + 1 is issued as soon as block ci sits in the staging tile)
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci) {
         const int c0 = ci * 32;
         if (c0 < prm.n) {
-          uint32_t rg[32];
-          tmem_ld32(taddr + c0, rg);
+          const long long t0 = tm ? clock64() : 0;
+          float4 b[8], us[8];                          // all look-ups BEFORE the staging stores: the compiler cannot tell that the two
+#pragma unroll                                         // shared-memory regions are disjoint and would serialise load -> store otherwise
+          for (int v = 0; v < 8; ++v) {                // (same address in every lane: broadcast)
+            b[v] = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * v);
+            us[v] = *reinterpret_cast<const float4*>(s_us + c0 + 4 * v);
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int v = 0; v < 8; ++v)
-            *reinterpret_cast<float4*>(stg + lane * STG_ROW + v * 16) = make_float4(
-                __uint_as_float(rg[4 * v]), __uint_as_float(rg[4 * v + 1]), __uint_as_float(rg[4 * v + 2]), __uint_as_float(rg[4 * v + 3]));
+          const long long t1 = tm ? clock64() : 0;
+          // the previous block's bulk store must have finished READING the staging tile before it is overwritten
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (prm.bias) b = __ldg(reinterpret_cast<const float4*>(prm.bias + c0) + so);
-          float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+          const long long t2 = tm ? clock64() : 0;
+          if (tm) { w1 += t1 - t0; w2 += t2 - t1; }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = 4 * j + sq;
-            if (row0 + rr < prm.m) {
-              float4 o = *reinterpret_cast<const float4*>(stg + rr * STG_ROW + so * 16);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              *(reinterpret_cast<float4*>(prm.y + (size_t)(row0 + rr) * prm.n + c0) + so) = o;
-              ps[0] += o.x; ps[1] += o.y; ps[2] += o.z; ps[3] += o.w;
-              pq[0] = fmaf(o.x, o.x, pq[0]); pq[1] = fmaf(o.y, o.y, pq[1]); pq[2] = fmaf(o.z, o.z, pq[2]); pq[3] = fmaf(o.w, o.w, pq[3]);
-            }
+          for (int v = 0; v < 8; ++v) {
+            float4 o = make_float4(fmaf(__uint_as_float(rg[4 * v]), us[v].x, b[v].x), fmaf(__uint_as_float(rg[4 * v + 1]), us[v].y, b[v].y),
+                                   fmaf(__uint_as_float(rg[4 * v + 2]), us[v].z, b[v].z), fmaf(__uint_as_float(rg[4 * v + 3]), us[v].w, b[v].w));
+            if (!live) o = make_float4(0.f, 0.f, 0.f, 0.f);                               // (clipped by the store; zero for the column sums)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((v ^ (lane & 7)) << 4)) = o;
+          }
+          if (c0 + 32 < prm.n) tmem_ld32(taddr + c0 + 32, rg);
+          const long long t3 = tm ? clock64() : 0;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          const long long t4 = tm ? clock64() : 0;
+          if (tm) { w3 += t3 - t2; w4 += t4 - t3; }
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&map_y)),
+                         "r"(smem_u32(stg)), "r"(c0), "r"((int)row0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           if (ci < 4 && prm.stats) {
+            float sa = 0.f, sq = 0.f;                  // column c0 + lane over the warp's 32 rows (conflict-free: a row's 32 words cover all banks)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              acc_s[ci & 3][e] += (double)ps[e];
-              acc_q[ci & 3][e] += (double)pq[e];
+            for (int r = 0; r < 32; ++r) {
+              const float v = *reinterpret_cast<const float*>(stg + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+              sa += v;
+              sq = fmaf(v, v, sq);
             }
+            acc_s[ci & 3] += (double)sa;
+            acc_q[ci & 3] += (double)sq;
           }
-          __syncwarp();                                  // the next chunk overwrites the staging tile
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[s]);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // all bulk stores of this warp complete
+    __syncwarp();
     if (prm.stats) {
-      // column totals of this CTA: lanes with the same column quad (so) hold disjoint rows -> add over sq (lane bits 3,4),
-      // then over the four epilogue warps in warp order through shared memory; one fp64 record per CTA
+      // per-CTA fp64 record: the four epilogue warps' column totals added in warp order through shared memory (the bits slots
+      // are free by now: every tile of this CTA has been expanded and multiplied)
+      double* sst = reinterpret_cast<double*>(smem_bits);              // [4 warps][2][128]
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
+      for (int ci = 0; ci < 4; ++ci)
         if (ci * 32 < prm.n) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            double a = acc_s[ci][e], b = acc_q[ci][e];
-            a += __shfl_xor_sync(FULL, a, 8);  b += __shfl_xor_sync(FULL, b, 8);
-            a += __shfl_xor_sync(FULL, a, 16); b += __shfl_xor_sync(FULL, b, 16);
-            if (sq == 0) {
-              s_stat[q][0][so * 4 + e] = a;
-              s_stat[q][1][so * 4 + e] = b;
-            }
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (q == 0) {
-            double* rec = prm.stats + (size_t)blockIdx.x * 2 * prm.n;
-            const int col = lane;
-            rec[ci * 32 + col] = ((s_stat[0][0][col] + s_stat[1][0][col]) + s_stat[2][0][col]) + s_stat[3][0][col];
-            rec[prm.n + ci * 32 + col] = ((s_stat[0][1][col] + s_stat[1][1][col]) + s_stat[2][1][col]) + s_stat[3][1][col];
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          sst[(q * 2 + 0) * 128 + ci * 32 + lane] = acc_s[ci];
+          sst[(q * 2 + 1) * 128 + ci * 32 + lane] = acc_q[ci];
         }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (q == 0) {
+        double* rec = prm.stats + (size_t)blockIdx.x * 2 * prm.n;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+          if (ci * 32 < prm.n) {
+            const int col = ci * 32 + lane;
+            rec[col] = ((sst[col] + sst[2 * 128 + col]) + sst[4 * 128 + col]) + sst[6 * 128 + col];
+            rec[prm.n + col] = ((sst[128 + col] + sst[3 * 128 + col]) + sst[5 * 128 + col]) + sst[7 * 128 + col];
+          }
       }
     }
   }
@@ -336,6 +521,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
     prm.dbg_out[warp * 4 + 0] = w0;
     prm.dbg_out[warp * 4 + 1] = w1;
     prm.dbg_out[warp * 4 + 2] = clock64() - t_begin;
+    prm.dbg_out[warp * 4 + 3] = w2;
+    if (warp == 4) { prm.dbg_out[60] = w3; prm.dbg_out[61] = w4; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -367,6 +554,7 @@ struct AdjTParams {
   int tmem_cols;
   int xstages;
   int ones;                            // 1: one more 32-column block whose first column is 1 -> column sums of X
+  int dbg;                             // diagnosis only (B2G_ADJT_DBG): 1 = skip the bit expansion, 2 = skip the X loads, 4 = skip the bits loads
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn32(uint32_t smem_addr) {
@@ -436,11 +624,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
       uint32_t ph = 1;
       for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         mbar_wait(&bar_xempty[s], ph);
-        mbar_expect_tx(&bar_xfull[s], xs_bytes);
+        const bool ldx = !(prm.dbg & 2);
+        mbar_expect_tx(&bar_xfull[s], ldx ? xs_bytes : 0u);
         uint8_t* st = base + (size_t)s * xs_bytes;
-        for (int c = 0; c < 4; ++c) tma_load_2d(st + c * AT_SUB, &map_x, &bar_xfull[s], c * KB, (int)(t * AT_ROWS));
-        if (prm.xb)
-          for (int c = 0; c < 4; ++c) tma_load_2d(st + a_bytes + c * AT_SUB, &map_b, &bar_xfull[s], c * KB, (int)(t * AT_ROWS));
+        if (ldx) {
+          for (int c = 0; c < 4; ++c) tma_load_2d(st + c * AT_SUB, &map_x, &bar_xfull[s], c * KB, (int)(t * AT_ROWS));
+          if (prm.xb)
+            for (int c = 0; c < 4; ++c) tma_load_2d(st + a_bytes + c * AT_SUB, &map_b, &bar_xfull[s], c * KB, (int)(t * AT_ROWS));
+        }
         if (++s == nxs) { s = 0; ph ^= 1; }
       }
     }
@@ -491,7 +682,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
     const int64_t tstep = (int64_t)gridDim.x * AT_BSTAGES;
     auto load_row = [&](int64_t t, uint32_t (&w)[WPE], float (&sc)[LY_MAXREL]) {
       const int64_t row = t * AT_ROWS + lane;
-      const bool live = t < n_tiles && row < prm.m;
+      const bool live = t < n_tiles && row < prm.m && !(prm.dbg & 4);
 #pragma unroll
       for (int i = 0; i < WPE; ++i) {
         const int k = j4 + i * AT_GROUP;
@@ -510,7 +701,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
 #pragma unroll
       for (int i = 0; i < WPE; ++i) {
         const int k = j4 + i * AT_GROUP;
-        if (k < nw) {
+        if (k < nw && !(prm.dbg & 1)) {
           uint8_t* brow = bst + (size_t)k * AT_SUB + lane * 128;
           const uint32_t word = wcur[i];
           const int split = prm.bl.split[k];
@@ -519,8 +710,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                // 32-byte chunk j (8 columns) at chunk j ^ (row & 3)
               uint8_t* dst = brow + ((j ^ (lane & 3)) << 5);
-              *reinterpret_cast<uint4*>(dst) = expand4(word, 8 * j, sa);        // (ALU expansion: a shared-memory look-up table, as in
-              *reinterpret_cast<uint4*>(dst + 16) = expand4(word, 8 * j + 4, sa);   //  k_layer_tf32, measured 25 % slower in this kernel)
+              *reinterpret_cast<uint4*>(dst) = expand4(word, 8 * j, sa);        // (ALU expansion: a shared-memory look-up table
+              *reinterpret_cast<uint4*>(dst + 16) = expand4(word, 8 * j + 4, sa);   //  measured 25 % slower in this kernel)
             }
           } else {
             const uint32_t sb = __float_as_uint(pick_scale(scur, prm.bl.rel_b[k]));
@@ -666,6 +857,34 @@ __global__ void __launch_bounds__(256) k_cat_weights(const __grid_constant__ Cat
   out[(size_t)j * p.ktot + k] = v;
 }
 
+// half mode of k_layer_tf32: the adjacency columns of row j (= output column j of the layer) as fp16 with a power-of-two
+// scale 2^e_j that puts the row's largest magnitude into [2^13, 2^14) -- fp16 keeps 11 significant bits (round to nearest;
+// TF32 as the tensor core reads it keeps 11 with truncation) but only 5 exponent bits, and backward rows are gradients of
+// any magnitude.  The dense columns [0, kx) are multiplied by the same 2^e_j (exact), unscale[j] = 2^-e_j undoes it in the
+// epilogue.  One warp per row: no atomics, no cross-CTA dependency.
+__global__ void __launch_bounds__(256) k_cat_half(float* __restrict__ wcat, int n, int kx, int ktot, int kh, __half* __restrict__ whalf,
+                                                  float* __restrict__ unscale) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= n) return;
+  float* row = wcat + (size_t)j * ktot;
+  float mx = 0.f;
+  for (int k = kx + lane; k < ktot; k += 32) mx = fmaxf(mx, fabsf(row[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+  int e = 0;
+  if (mx > 0.f && mx <= 3.0e38f) {
+    int q;
+    frexpf(mx, &q);                                   // mx = f 2^q, f in [0.5, 1)
+    e = 14 - q;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  }
+  const float sc = ldexpf(1.f, e);
+  __half* hrow = whalf + (size_t)j * kh;
+  for (int c = lane; c < kh; c += 32) hrow[c] = __float2half_rn(kx + c < ktot ? row[kx + c] * sc : 0.f);
+  for (int k = lane; k < kx; k += 32) row[k] *= sc;
+  if (lane == 0) unscale[j] = ldexpf(1.f, -e);
+}
+
 // sums[2n] (fp64) = per-CTA records [n_cta][2][n] added in CTA order
 __global__ void __launch_bounds__(256) k_stats_reduce(const double* __restrict__ rec, int n_cta, int n2, double* __restrict__ sums) {
   __shared__ double sh[8][32];
@@ -701,10 +920,14 @@ int fill_layout(BitLayout* bl, const b2g_bit_layout_t* h) {
   return B2G_OK;
 }
 
-inline size_t layer_smem(int n, int stages) { return (size_t)stages * (A_CHUNK + (size_t)n * KB * 4) + STG_BYTES + 1024; }
-inline int layer_stages(int n) {
+inline size_t layer_smem(int n, int stages, int nw) {
+  size_t slots = 2 * ((size_t)TILE_M * nw * 4 + LY_MAXREL * TILE_M * 4);
+  if (slots < 8192) slots = 8192;                    // (the statistics exchange at the end of the kernel reuses the slots)
+  return (size_t)stages * (A_CHUNK + (size_t)n * KB * 4) + STG_BYTES + 2048 + slots + 1024;
+}
+inline int layer_stages(int n, int nw) {
   int st = LY_MAX_STAGES;
-  while (st > 0 && layer_smem(n, st) > 227 * 1024) --st;
+  while (st > 0 && layer_smem(n, st, nw) > 227 * 1024 - 1024) --st;     // (1024: the kernel's static shared memory)
   return st;
 }
 }  // namespace
@@ -744,34 +967,58 @@ extern "C" int b2g_layer_cat_weights(const float* const* h_ws, int n_w, int w_tr
   return B2G_OK;
 }
 
+extern "C" int b2g_layer_cat_half(float* wcat, int n, int kx, int ktot, uint16_t* whalf, float* unscale, void* stream_) {
+  B2G_CHECK_ARG(wcat && whalf && unscale && n > 0 && kx >= 0 && ktot > kx && ((ktot - kx) % 32) == 0 && (ktot - kx) / 32 <= LY_MAXW,
+                "layer_cat_half: bad args");
+  B2G_CHECK_ARG(aligned16(whalf), "layer_cat_half: whalf must be 16-byte aligned");
+  const int kh = 64 * (((ktot - kx) / 32 + 1) / 2);
+  k_cat_half<<<(unsigned)ceil_div(n, 8), 256, 0, (cudaStream_t)stream_>>>(wcat, n, kx, ktot, kh, reinterpret_cast<__half*>(whalf), unscale);
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
 extern "C" int b2g_layer_fwd_tc_supported(int64_t m, int n, int kx, int nw) {
   if (m < 1 || n < 32 || n > 256 || (n % 32) != 0 || kx < 0 || (kx % 32) != 0 || nw < 1 || nw > LY_MAXW) return 0;
-  return layer_stages(n) >= 2 ? 1 : 0;
+  return layer_stages(n, nw) >= 2 ? 1 : 0;
 }
 extern "C" size_t b2g_layer_stats_ws_bytes(int n) { return ((size_t)sm_count() * 2 * n + 2 * n) * sizeof(double) + 256; }
 
-extern "C" int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* bias, const uint32_t* bits,
+extern "C" int b2g_layer_fwd_tc(const float* x, const float* wcat, const uint16_t* whalf, const float* unscale, const float* bias,
+                                const uint32_t* bits,
                                 const b2g_bit_layout_t* h_layout, const float* const* h_rscale, int64_t m, int n, int kx, float* y,
                                 double* stat_sums, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(wcat && bits && y && h_layout && b2g_layer_fwd_tc_supported(m, n, kx, h_layout->nw) && (kx == 0 || x),
                 "layer_fwd_tc: unsupported shape m=%lld n=%d kx=%d", (long long)m, n, kx);
-  B2G_CHECK_ARG(aligned16(x) && aligned16(wcat) && aligned16(y) && (!bias || aligned16(bias)), "layer_fwd_tc: pointers must be 16-byte aligned");
+  B2G_CHECK_ARG(aligned16(x) && aligned16(wcat) && aligned16(y) && (!bias || aligned16(bias)) && aligned16(bits), "layer_fwd_tc: pointers must be 16-byte aligned");
+  B2G_CHECK_ARG((whalf == nullptr) == (unscale == nullptr) && aligned16(whalf) && aligned16(unscale), "layer_fwd_tc: whalf / unscale (both or neither, 16-byte aligned)");
   LayerParams prm{};
   int rc = fill_layout(&prm.bl, h_layout);
   if (rc) return rc;
   const int ktot = kx + 32 * prm.bl.nw;
-  CUtensorMap map_x, map_w;
+  CUtensorMap map_x, map_w, map_h;
   rc = make_map(&map_x, kx > 0 ? x : wcat, kx > 0 ? m : n, kx > 0 ? kx : ktot, TILE_M);     // (kx == 0: never dereferenced)
   if (rc) return rc;
   rc = make_map(&map_w, wcat, n, ktot, n);
   if (rc) return rc;
+  map_h = map_w;                                                                            // (tf32 mode: never dereferenced)
+  if (whalf) {
+    rc = make_map_f16(&map_h, whalf, n, 64 * ((prm.bl.nw + 1) / 2), n);
+    if (rc) return rc;
+  }
+  CUtensorMap map_y;
+  rc = make_map(&map_y, y, m, n, 32);
+  if (rc) return rc;
+  prm.half_adj = whalf ? 1 : 0;
+  prm.unscale = unscale;
+  for (int r = 0; r < LY_MAXREL && h_rscale; ++r)
+    B2G_CHECK_ARG(aligned16(h_rscale[r]), "layer_fwd_tc: row scale %d must be 16-byte aligned", r);
   prm.bits = bits; prm.bias = bias; prm.y = y; prm.m = m; prm.n = n; prm.kx = kx;
   for (int r = 0; r < LY_MAXREL; ++r) prm.rscale[r] = h_rscale ? h_rscale[r] : nullptr;
   int cols = 32;
   while (cols < 2 * n) cols <<= 1;
   prm.tmem_cols = cols;
-  prm.stages = layer_stages(n);
+  prm.stages = layer_stages(n, prm.bl.nw);
   {
     const char* e = getenv("B2G_LAYER_DBG");
     prm.dbg = e ? atoi(e) : 0;
@@ -789,7 +1036,7 @@ extern "C" int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* 
     }
     prm.stats = (double*)ws;
   }
-  const size_t smem = layer_smem(n, prm.stages);
+  const size_t smem = layer_smem(n, prm.stages, prm.bl.nw);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     B2G_CUDA(cudaFuncSetAttribute(k_layer_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -801,14 +1048,15 @@ extern "C" int b2g_layer_fwd_tc(const float* x, const float* wcat, const float* 
     B2G_CUDA(cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), st));
     prm.dbg_out = dbg_buf;
   }
-  k_layer_tf32<<<grid, LY_THREADS, smem, st>>>(map_x, map_w, prm);
+  k_layer_tf32<<<grid, LY_THREADS, smem, st>>>(map_x, map_w, map_h, map_y, prm);
   B2G_LAUNCH_CHECK();
   if (prm.dbg & 8) {
     long long h[64];
     B2G_CUDA(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
     B2G_CUDA(cudaStreamSynchronize(st));
-    fprintf(stderr, "[k_layer_tf32 CTA0 cycles] total %lld | TMA wait-empty %lld | MMA wait-full %lld wait-tempty %lld | epi(w4) wait-tfull %lld | "
-            "exp(w8) wait-empty(adj) %lld wait-empty(x) %lld\n", h[0 * 4 + 2], h[0], h[1 * 4], h[1 * 4 + 1], h[4 * 4], h[8 * 4], h[8 * 4 + 1]);
+    fprintf(stderr, "[k_layer_tf32 CTA0 cycles] total %lld | TMA wait-empty %lld | MMA wait-full(x) %lld (adj) %lld wait-tempty %lld | epi(w4) wait-tfull %lld | "
+            "exp(w8) wait-empty %lld wait-bits %lld | epi(w4) tcgen05.ld+wait %lld, wait_group.read %lld, fma+sts %lld, fence+syncwarp %lld\n", h[0 * 4 + 2], h[0], h[1 * 4], h[1 * 4 + 3],
+            h[1 * 4 + 1], h[4 * 4], h[8 * 4], h[8 * 4 + 1], h[4 * 4 + 1], h[4 * 4 + 3], h[60], h[61]);
   }
   if (stat_sums) {
     k_stats_reduce<<<(unsigned)ceil_div(2 * n, 32), 256, 0, st>>>(prm.stats, grid, 2 * n, stat_sums);
@@ -863,6 +1111,10 @@ extern "C" int b2g_layer_adjT_tc(const float* x, const uint32_t* bits, const b2g
   while (cols < prm.dcols) cols <<= 1;
   prm.tmem_cols = cols;
   prm.xstages = adjT_xstages(nsub, prm.xb);
+  {
+    const char* e = getenv("B2G_ADJT_DBG");
+    prm.dbg = e ? atoi(e) : 0;
+  }
   B2G_CHECK_ARG(prm.xstages >= 2, "layer_adjT_tc: shared memory too small for nw=%d", nw);
   const size_t smem = (size_t)prm.xstages * (4 + 4 * prm.xb) * AT_SUB + (size_t)AT_BSTAGES * nsub * AT_SUB + 1024;
   static size_t smem_set = 0;

@@ -872,15 +872,31 @@ def layer_cat_weights_(ws_list, transposed, tabs, scales, offs, kx, ktot, n, bia
     return out, bias_out
 
 
-def layer_fwd_tc_(x, wcat, bias, bits, pb, rscales, y, stat_sums=None):
+LAYER_HALF = os.environ.get("B2G_LAYER_HALF", "1") != "0"      # adjacency part of k_layer_tf32 as fp16 {0 | 1/deg} (kind::f16)
+
+
+def layer_cat_half_(wcat, kx):
+    """(whalf [n, 64 ceil(nw/2)] fp16, unscale [n]) of b2g_layer_cat_half; scales wcat[:, :kx] in place"""
+    lib = _lib.load()
+    n, ktot = wcat.shape
+    kh = 64 * (((ktot - kx) // 32 + 1) // 2)
+    whalf = torch.empty((n, kh), dtype=torch.float16, device=wcat.device)
+    unscale = torch.empty(n, dtype=torch.float32, device=wcat.device)
+    _run("b2g_layer_cat_half", lib.b2g_layer_cat_half, wcat.data_ptr(), n, kx, ktot, whalf.data_ptr(), unscale.data_ptr(), _stream())
+    return whalf, unscale
+
+
+def layer_fwd_tc_(x, wcat, bias, bits, pb, rscales, y, stat_sums=None, half=None):
+    """half: None -> TF32 adjacency tiles; (whalf, unscale) from layer_cat_half_ -> fp16 adjacency tiles"""
     lib = _lib.load()
     m, kx = x.shape
     n = wcat.shape[0]
     ws = None
     if stat_sums is not None:
         ws = workspace(lib.b2g_layer_stats_ws_bytes(n), x.device)
+    whalf, unscale = half if half is not None else (None, None)
     cost(4 * (m * kx + m * n) + 4 * m * pb.nw + 4 * wcat.numel(), 2 * m * n * wcat.shape[1])
-    _run("b2g_layer_fwd_tc", lib.b2g_layer_fwd_tc, x.data_ptr(), wcat.data_ptr(), _ptr(bias), bits.data_ptr(), ctypes.byref(pb.layout),
+    _run("b2g_layer_fwd_tc", lib.b2g_layer_fwd_tc, x.data_ptr(), wcat.data_ptr(), _ptr(whalf), _ptr(unscale), _ptr(bias), bits.data_ptr(), ctypes.byref(pb.layout),
          _ptr_array(list(rscales) + [None] * (4 - len(rscales))), m, n, kx, y.data_ptr(), _ptr(stat_sums), _ptr(ws),
          0 if ws is None else ws.numel(), _stream())
     return y
@@ -937,7 +953,8 @@ class PatientSideFn(Function):
         out = torch.empty((m, d), dtype=torch.float32, device=x_p.device)
         if pb.bits_in is not None and any(y is not None for y in ys_in):
             sums = torch.empty(2 * d, dtype=torch.float64, device=x_p.device) if (want_stats and d <= 128) else None
-            layer_fwd_tc_(x_p, wcat, bias, pb.bits_in, pb, pb.rscale_in(), out, sums)
+            half = layer_cat_half_(wcat, d) if LAYER_HALF else None
+            layer_fwd_tc_(x_p, wcat, bias, pb.bits_in, pb, pb.rscale_in(), out, sums, half)
             if sums is not None:
                 _tag_bnsums(out, sums)          # BatchNorm statistics of the layer output (model.py:259-261) for free
         else:
@@ -979,7 +996,8 @@ class PatientSideFn(Function):
             if pb.bits_out is not None and any(g is not None for g in live_aggs):
                 wcat, _ = layer_cat_weights_(w_roots, True, live_aggs, pb.inv_deg_out(), pb.offs, d, ktot, d)
                 dx = torch.empty_like(x_p)
-                layer_fwd_tc_(dout_x, wcat, None, pb.bits_out, pb, [None] * nt, dx)
+                half = layer_cat_half_(wcat, d) if LAYER_HALF else None
+                layer_fwd_tc_(dout_x, wcat, None, pb.bits_out, pb, [None] * nt, dx, None, half)
             elif dout is not None:
                 w = w_roots[0]
                 for extra in w_roots[1:]:

@@ -67,10 +67,11 @@ def _random_hub(G, m, sizes, density, dev, seed=0):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("half", [False, True], ids=["tf32adj", "f16adj"])
 @pytest.mark.parametrize("m,sizes,density", [(128, [50, 200, 100], [0.2, 0.01, 0.03]), (1000, [20, 30, 25], [0.5, 0.2, 0.3]),
                                              (4099, [160, 200, 100], [0.67, 0.05, 0.28]), (70001, [50, 200, 100], [0.4, 0.01, 0.05]),
                                              (777, [5, 5, 5, 40], [0.5, 0.5, 0.5, 0.1]), (300, [300], [0.1])])
-def test_layer_fwd_tc(m, sizes, density, pkg):
+def test_layer_fwd_tc(m, sizes, density, half, pkg):
     G, ops, _, _, L = _mods()
     dev = torch.device("cuda:0")
     dense, pb = _random_hub(G, m, sizes, density, dev, seed=m)
@@ -81,6 +82,9 @@ def test_layer_fwd_tc(m, sizes, density, pkg):
     w2 = torch.randn(d, d, generator=gen) / d ** 0.5
     b1, b2 = torch.randn(d, generator=gen), torch.randn(d, generator=gen)
     ys = [torch.randn(n, d, generator=gen) for n in sizes]
+    if half:
+        ys[-1] = ys[-1] * 3e-9                # rows of any magnitude (backward: gradients) must survive the fp16 B operand
+        ys[0][:, 5] = 0.0
     rs = [1.0 / a.sum(1).clamp(min=1) for a in dense]
     # library result
     wcat, bias = ops.layer_cat_weights_([w.to(dev), w2.to(dev)], False, [y.to(dev) for y in ys], [None] * len(sizes), pb.offs, d,
@@ -94,16 +98,34 @@ def test_layer_fwd_tc(m, sizes, density, pkg):
         torch.testing.assert_close(a.cpu(), b, rtol=0, atol=0)
     out = torch.full((m, d), float("nan"), device=dev)
     sums = torch.zeros(2 * d, dtype=torch.float64, device=dev)
-    ops.layer_fwd_tc_(x.to(dev), wcat, bias, pb.bits_in, pb, rs_lib, out, sums)
+    hv = None
+    if half:
+        # b2g_layer_cat_half: per output column j a power-of-two scale puts max_t |Y[t, j]| into [2^13, 2^14); fp16, round to nearest
+        wcat0 = wcat.clone()
+        hv = ops.layer_cat_half_(wcat, d)
+        whalf, unscale = hv
+        ycat = torch.cat(ys, 0)                                     # [sum n, d]
+        mant, expo = torch.frexp(ycat.abs().max(0).values)
+        e_j = torch.where(ycat.abs().max(0).values > 0, 14 - expo, torch.zeros_like(expo)).double()
+        sc_j = torch.pow(torch.tensor(2.0, dtype=torch.float64), e_j)
+        torch.testing.assert_close(unscale.cpu().double(), 1.0 / sc_j, rtol=0, atol=0)
+        assert torch.equal(wcat[:, :d].cpu().double(), wcat0[:, :d].cpu().double() * sc_j[:, None])
+        for y, off, n in zip(ys, pb.offs, sizes):
+            assert torch.equal(whalf[:, off:off + n].cpu().double(), (y.double() * sc_j[None, :]).half().double().t())
+        assert whalf.shape[1] == 64 * ((pb.nw + 1) // 2)
+    ops.layer_fwd_tc_(x.to(dev), wcat, bias, pb.bits_in, pb, rs_lib, out, sums, hv)
     torch.cuda.synchronize()
     # references
     ref = x.double() @ (w + w2).double().t() + (b1 + b2).double()
     ref_t = tf32_trunc(x).double() @ tf32_trunc(w + w2).double().t() + (b1 + b2).double()
     for a, r, y in zip(dense, rs, ys):
         ref += (a.double() * r.double()[:, None]) @ y.double()
-        ref_t += (a.double() * tf32_trunc(r).double()[:, None]) @ tf32_trunc(y).double()
+        if half:
+            ref_t += (a.double() * r.half().double()[:, None]) @ ((y.double() * sc_j[None, :]).half().double() / sc_j[None, :])
+        else:
+            ref_t += (a.double() * tf32_trunc(r).double()[:, None]) @ tf32_trunc(y).double()
     assert torch.isfinite(out).all()
-    assert relmax(out, ref_t) < 2e-5, "tcgen05 result differs from the TF32-truncated float64 product"
+    assert relmax(out, ref_t) < 2e-5, "tcgen05 result differs from the float64 product of the operands as the tensor core reads them"
     assert relmax(out, ref) < 3e-3
     # BatchNorm column statistics from the epilogue
     o64 = out.double().cpu()
@@ -111,8 +133,18 @@ def test_layer_fwd_tc(m, sizes, density, pkg):
     torch.testing.assert_close(sums[d:].cpu(), (o64 * o64).sum(0), rtol=1e-6, atol=1e-6 * m)
     # deterministic
     out2 = torch.empty_like(out)
-    ops.layer_fwd_tc_(x.to(dev), wcat, bias, pb.bits_in, pb, rs_lib, out2)
+    ops.layer_fwd_tc_(x.to(dev), wcat, bias, pb.bits_in, pb, rs_lib, out2, None, hv)
     assert torch.equal(out, out2)
+    if half:
+        # the contribution of the tiny-magnitude relation alone (x part and the other relations zeroed): relative precision kept
+        y_only = [torch.zeros_like(y) for y in ys[:-1]] + [ys[-1]]
+        wz, _ = ops.layer_cat_weights_([torch.zeros(d, d, device=dev)], False, [y.to(dev) for y in y_only], [None] * len(sizes), pb.offs, d,
+                                       d + 32 * pb.nw, d, [])
+        hz = ops.layer_cat_half_(wz, d)
+        out3 = torch.empty_like(out)
+        ops.layer_fwd_tc_(x.to(dev), wz, None, pb.bits_in, pb, rs_lib, out3, None, hz)
+        ref3 = (dense[-1].double() * rs[-1].double()[:, None]) @ ys[-1].double()
+        assert relmax(out3, ref3) < 2e-3, "small-magnitude rows lost in the fp16 operand"
 
 
 @pytest.mark.gpu

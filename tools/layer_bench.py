@@ -75,7 +75,11 @@ def main():
         out = torch.empty(m, d, device=dev)
         sums = torch.zeros(2 * d, dtype=torch.float64, device=dev)
         rs = pb.rscale_in()
+        wcat_h = wcat.clone()
+        hv = ops.layer_cat_half_(wcat_h, d)
         for name, fn, nbytes in [
+            ("k_layer_tf32 (f16 adjacency)", lambda: ops.layer_fwd_tc_(x, wcat_h, bias, pb.bits_in, pb, rs, out, None, hv), 8 * m * d + 4 * m * pb.nw),
+            ("k_layer_tf32 (f16 adjacency)+stats", lambda: ops.layer_fwd_tc_(x, wcat_h, bias, pb.bits_in, pb, rs, out, sums, hv), 8 * m * d + 4 * m * pb.nw),
             ("k_layer_tf32", lambda: ops.layer_fwd_tc_(x, wcat, bias, pb.bits_in, pb, rs, out), 8 * m * d + 4 * m * pb.nw),
             ("k_layer_tf32+stats", lambda: ops.layer_fwd_tc_(x, wcat, bias, pb.bits_in, pb, rs, out, sums), 8 * m * d + 4 * m * pb.nw),
             ("k_adjT_tf32", lambda: ops.layer_adjT_tc_(x, pb.bits_out, pb, [None] * len(ys), pb.col_scale_out()), 4 * m * d + 4 * m * pb.nw),
