@@ -108,6 +108,13 @@ typedef struct {
 int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_rows, int d, float* out,
                       int accumulate, void* stream);
 
+/* The same contraction (identical arithmetic and edge order) with every SOURCE TABLE STAGED IN SHARED MEMORY by bulk copies
+ * (cp.async.bulk + mbarrier), one resident CTA per SM: for patient destinations, whose sources are the few-hundred-row lab /
+ * diagnosis / medication tables (north_star (b)).  h_n_src[k] = rows of rels[k].x; supported when they sum to <= 200 KB. */
+int b2g_gather_reduce_staged_supported(const int* h_n_src, int n_rels, int d);
+int b2g_gather_reduce_staged(const b2g_rel_t* h_rels, const int* h_n_src, int n_rels, int64_t n_rows, int d, float* out,
+                             int accumulate, void* stream);
+
 /* Same contraction for LONG rows (type destinations).  Two deterministic phases: one warp per chunk
  * item writes a partial row into ws, then one warp per output row adds its partials in item order.
  * ws: n_items * d * 4 bytes. */

@@ -1,7 +1,7 @@
 // Segmented gather-reduce over CSR (the message-passing contraction) and row gathers.
 // Replaces SAGEConv.propagate's index_select -> [E,d] message tensor -> scatter_add (PyG; model.py:256):
 // no message tensor is ever materialised and no floating-point atomics are used.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 using namespace b2g;
@@ -68,6 +68,133 @@ __global__ void __launch_bounds__(256) k_gather_reduce(RelPack rels, int n_rels,
     acc.add(prev);
   }
   acc.store(o, lane);
+}
+
+// ---- the same contraction with the SOURCE TABLES STAGED IN SHARED MEMORY ---------------------------------------------------
+// Patient destinations gather from the lab / diagnosis / medication tables, a few hundred rows each (C4: 50 + 200 + 100 rows
+// of 512 B = 175 KB): every CTA brings all of them into shared memory once with bulk copies (cp.async.bulk + mbarrier) and
+// stays resident (one CTA per SM, grid-stride over the destination rows); a gathered row is then one conflict-free LDS.128
+// per lane instead of a trip through the L1 tags.  Same arithmetic and edge order as k_gather_reduce: identical results.
+struct StagedInfo {
+  int n_src[4];
+  int off[4];          // float offset of table k in shared memory
+};
+
+template <int D>
+__device__ __forceinline__ void lds_row(RowVec<D>& r, const float* row, int lane) {
+  if constexpr (D >= 128) {
+#pragma unroll
+    for (int j = 0; j < D / 128; ++j) {
+      const float4 t = *(reinterpret_cast<const float4*>(row + j * 128) + lane);
+      r.v[4 * j] = t.x; r.v[4 * j + 1] = t.y; r.v[4 * j + 2] = t.z; r.v[4 * j + 3] = t.w;
+    }
+  } else if constexpr (D == 64) {
+    const float2 t = *(reinterpret_cast<const float2*>(row) + lane);
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = row[lane];
+  }
+}
+
+// A warp owns 32 consecutive destination rows: their row pointers are one coalesced load per relation, and their column
+// indices are one contiguous stream per relation that the warp walks in 32-entry chunks held in registers (current + next
+// chunk, the next one always in flight), so no global-load latency sits between two rows; the gathered rows themselves are
+// LDS.128 from the staged tables, four in flight.  FMAs are applied in edge order, relation by relation: bit-identical to
+// k_gather_reduce.
+template <int D>
+__global__ void __launch_bounds__(512, 1) k_gather_reduce_staged(RelPack rels, StagedInfo info, int n_rels, int64_t n_rows,
+                                                                 float* __restrict__ out, int accumulate) {
+  extern __shared__ __align__(16) float tab[];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int k = 0; k < n_rels; ++k) total += (uint32_t)info.n_src[k] * D * 4u;
+    mbar_expect_tx(&bar, total);
+    for (int k = 0; k < n_rels; ++k) bulk_load(tab + info.off[k], rels.r[k].x, (uint32_t)info.n_src[k] * D * 4u, &bar);
+  }
+  mbar_wait(&bar, 0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int64_t n_blocks = (n_rows + 31) / 32;
+  for (int64_t blk = (int64_t)blockIdx.x * nwarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * nwarps) {
+    const int64_t row0 = blk * 32;
+    const int nr = (int)min((int64_t)32, n_rows - row0);
+    int rp[4], eblk[4], base[4], buf[4], nxt[4], cur[4];
+    float rsv[4], sbuf[4], snxt[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < n_rels) {
+        const b2g_rel_t& rel = rels.r[k];
+        rp[k] = __ldg(rel.rowptr + row0 + min(lane, nr));
+        eblk[k] = __ldg(rel.rowptr + row0 + nr);
+        rsv[k] = (rel.row_scale && lane < nr) ? __ldg(rel.row_scale + row0 + lane) : 1.0f;
+        base[k] = __shfl_sync(FULL, rp[k], 0);
+        cur[k] = 0;
+        const int j0 = base[k] + lane, j1 = base[k] + 32 + lane;
+        buf[k] = j0 < eblk[k] ? __ldg(rel.col + j0) : 0;
+        nxt[k] = j1 < eblk[k] ? __ldg(rel.col + j1) : 0;
+        sbuf[k] = (rel.col_scale && j0 < eblk[k]) ? __ldg(rel.col_scale + buf[k]) : 1.0f;
+        snxt[k] = (rel.col_scale && j1 < eblk[k]) ? __ldg(rel.col_scale + nxt[k]) : 1.0f;
+      }
+    }
+    for (int r = 0; r < nr; ++r) {
+      RowVec<D> acc;
+      acc.zero();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < n_rels) {
+          const b2g_rel_t& rel = rels.r[k];
+          const float* src = tab + info.off[k];
+          const int b = __shfl_sync(FULL, rp[k], r);
+          const int e = r + 1 < 32 ? __shfl_sync(FULL, rp[k], r + 1) : eblk[k];
+          RowVec<D> part;
+          part.zero();
+          for (int j = b; j < e; j += 4) {
+            const int idx = j - base[k];
+            while ((idx >> 5) > cur[k]) {                  // (uniform) step to the chunk of edge j; keep the one after it in flight
+              buf[k] = nxt[k];
+              sbuf[k] = snxt[k];
+              ++cur[k];
+              const int jn = base[k] + (cur[k] + 1) * 32 + lane;
+              nxt[k] = jn < eblk[k] ? __ldg(rel.col + jn) : 0;
+              snxt[k] = (rel.col_scale && jn < eblk[k]) ? __ldg(rel.col_scale + nxt[k]) : 1.0f;
+            }
+            const int cnt = min(4, e - j);
+            int c[4];
+            float sc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int id = idx + u;
+              const bool in_next = (id >> 5) > cur[k];     // uniform: a group of 4 touches at most the current and the next chunk
+              c[u] = __shfl_sync(FULL, in_next ? nxt[k] : buf[k], id & 31);
+              sc[u] = __shfl_sync(FULL, in_next ? snxt[k] : sbuf[k], id & 31);
+            }
+            RowVec<D> rw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                  // (a zero column scale means "row not present", as in k_gather_reduce)
+              if (u < cnt && sc[u] != 0.f) lds_row<D>(rw[u], src + (size_t)c[u] * D, lane);
+              else rw[u].zero();
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (u < cnt) part.fma(sc[u], rw[u]);
+          }
+          acc.fma(__shfl_sync(FULL, rsv[k], r), part);
+        }
+      }
+      float* o = out + (size_t)(row0 + r) * D;
+      if (accumulate) {
+        RowVec<D> prev;
+        prev.load_rw(o, lane);
+        acc.add(prev);
+      }
+      acc.store(o, lane);
+    }
+  }
 }
 
 template <int D>
@@ -254,6 +381,49 @@ extern "C" int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_
   }
   unsigned grid = (unsigned)ceil_div(n_rows, 8);
   DISPATCH_D(d, (k_gather_reduce<D><<<grid, 256, 0, st>>>(pack, n_rels, n_rows, out, accumulate)));
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+/* all source tables in shared memory: 16-byte aligned tables, sum of rows * d * 4 <= 200 KB */
+extern "C" int b2g_gather_reduce_staged_supported(const int* h_n_src, int n_rels, int d) {
+  if (!h_n_src || n_rels < 1 || n_rels > 4 || (d != 32 && d != 64 && d != 128 && d != 256)) return 0;
+  size_t bytes = 0;
+  for (int k = 0; k < n_rels; ++k) {
+    if (h_n_src[k] < 1) return 0;
+    bytes += (size_t)h_n_src[k] * d * 4;
+  }
+  return bytes <= 200 * 1024 ? 1 : 0;
+}
+
+extern "C" int b2g_gather_reduce_staged(const b2g_rel_t* h_rels, const int* h_n_src, int n_rels, int64_t n_rows, int d, float* out,
+                                        int accumulate, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(h_rels && out && n_rows >= 0 && b2g_gather_reduce_staged_supported(h_n_src, n_rels, d),
+                "gather_reduce_staged: the source tables must fit 200 KB of shared memory (n_rels=%d d=%d)", n_rels, d);
+  B2G_CHECK_ARG(aligned16(out), "gather_reduce_staged: out not 16-byte aligned");
+  if (n_rows == 0) return B2G_OK;
+  RelPack pack{};
+  StagedInfo info{};
+  int off = 0;
+  for (int k = 0; k < n_rels; ++k) {
+    B2G_CHECK_ARG(h_rels[k].rowptr && h_rels[k].x && aligned16(h_rels[k].x), "gather_reduce_staged: relation %d has null/unaligned pointers", k);
+    pack.r[k] = h_rels[k];
+    info.n_src[k] = h_n_src[k];
+    info.off[k] = off;
+    off += h_n_src[k] * d;
+  }
+  const size_t smem = (size_t)off * 4;
+  int64_t blocks = ceil_div(n_rows, 32 * 16);
+  unsigned grid = (unsigned)(blocks < sm_count() ? blocks : sm_count());
+  DISPATCH_D(d, ({
+               static size_t smem_set = 0;
+               if (smem > smem_set) {
+                 B2G_CUDA(cudaFuncSetAttribute(k_gather_reduce_staged<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                 smem_set = smem;
+               }
+               k_gather_reduce_staged<D><<<grid, 512, smem, st>>>(pack, info, n_rels, n_rows, out, accumulate);
+             }));
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

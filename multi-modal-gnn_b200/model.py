@@ -27,6 +27,8 @@ import re
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -341,7 +343,7 @@ class HeteroRGCN(nn.Module):
         None when not applicable (the caller then runs the per-relation path)."""
         dctx = self.dist
         hub = dctx.sharded_type if dctx is not None else "patient"
-        if hub not in x or hub not in by_dst or ops.PRECISION != "tf32":
+        if hub not in x or hub not in by_dst or ops.PRECISION != "tf32" or os.environ.get("B2G_FUSED_LAYER", "1") == "0":
             return None
         pb = gi.hub_bits(hub)
         if not ops.patient_side_supported(pb, x[hub].shape[0], self.hidden_dim):

@@ -205,6 +205,13 @@ def small_colsum_group_(xs, outs):
         _run("b2g_small_colsum_group", lib.b2g_small_colsum_group, px, po, pm, pn, n, _stream())
 
 
+# b2g_gather_reduce_staged (source tables staged in shared memory) is bit-identical to b2g_gather_reduce and measured equal in
+# speed at the C4 shard (0.86 vs 0.81 ms: the 175 KB of tables are L1-resident for the plain kernel too, and both are bound by
+# the per-row dependency chain, profiles/r2_gather_bench_c4s8.json) -- opt-in with B2G_GATHER_STAGED=1
+GATHER_STAGED = os.environ.get("B2G_GATHER_STAGED", "0") == "1"
+STAGED_MIN_ROWS = 4096          # below this the one-off table copy per CTA costs more than the gathers save
+
+
 def gather_reduce_(csrs: Sequence[CSR], xs: Sequence[torch.Tensor], row_scales, col_scales, out: torch.Tensor,
                    accumulate: bool):
     """out[r] (+)= sum_k row_scale_k[r] * sum_{j in row r} col_scale_k[col_j] * x_k[col_j].  Short-row CSRs are
@@ -227,7 +234,12 @@ def gather_reduce_(csrs: Sequence[CSR], xs: Sequence[torch.Tensor], row_scales, 
         # algorithmic bytes: CSR indices once + output rows once (+ read when accumulating) + source tables once
         cost(sum(4 * (csrs[i].n_edges + csrs[i].n_rows + 1) + 4 * d * min(csrs[i].n_vals, csrs[i].n_edges) for i in grp)
              + 4 * n_rows * d * (2 if acc else 1), 2 * d * sum(csrs[i].n_edges for i in grp))
-        _run("b2g_gather_reduce", lib.b2g_gather_reduce, arr, len(grp), n_rows, d, out.data_ptr(), int(acc), _stream())
+        n_src = (ctypes.c_int * len(grp))(*[int(xs[i].shape[0]) for i in grp])
+        if GATHER_STAGED and n_rows >= STAGED_MIN_ROWS and lib.b2g_gather_reduce_staged_supported(n_src, len(grp), d):
+            # few-row source tables (lab / diagnosis / medication -> patient): staged in shared memory once per CTA
+            _run("b2g_gather_reduce_staged", lib.b2g_gather_reduce_staged, arr, n_src, len(grp), n_rows, d, out.data_ptr(), int(acc), _stream())
+        else:
+            _run("b2g_gather_reduce", lib.b2g_gather_reduce, arr, len(grp), n_rows, d, out.data_ptr(), int(acc), _stream())
         acc = True
     for i in long_:
         c = csrs[i]

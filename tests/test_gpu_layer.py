@@ -338,3 +338,43 @@ def test_linear_epilogue_statistics_and_l2norm(m, n, k, pkg):
         ops.L2NormFn.apply(ops.linear(xb, wb, bb), 1e-12).backward(go)
         for a_, b_ in ((xa, xb), (wa, wb), (ba, bb)):
             assert relmax(a_.grad, b_.grad) < 5e-4          # (the two forward results differ in the last bits: fused vs separate normalisation)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,sizes,density,d", [(5000, [50, 200, 100], [0.2, 0.01, 0.03], 128), (70001, [160, 200, 100], [0.3, 0.02, 0.1], 128),
+                                               (9000, [20, 30, 25], [0.5, 0.2, 0.3], 64), (6000, [300], [0.1], 256)])
+def test_gather_reduce_staged_equals_unstaged(m, sizes, density, d, pkg):
+    """b2g_gather_reduce_staged (source tables staged in shared memory by bulk copies, north_star (b)) computes the mean
+    aggregation onto the patient rows (PyG SAGEConv(aggr='mean').propagate, model.py:256) with the same arithmetic and edge
+    order as b2g_gather_reduce: bit-identical, and within 1e-5 of the float64 product."""
+    G, ops, _, _, L = _mods()
+    dev = torch.device("cuda:0")
+    dense, pb = _random_hub(G, m, sizes, density, dev, seed=m + 7)
+    gen = torch.Generator().manual_seed(5)
+    xs = [torch.randn(n, d, generator=gen) for n in sizes]
+    gi_rel = [rel for rel in pb.in_rel]
+    assert all(r is not None for r in gi_rel)
+    csrs = [r.by_dst for r in gi_rel]
+    rsc = [r.by_dst.inv_deg for r in gi_rel]
+    xd = [x.to(dev) for x in xs]
+    outs = {}
+    old = ops.GATHER_STAGED
+    try:
+        for staged in (False, True):
+            ops.GATHER_STAGED = staged
+            ops.PROFILE = []
+            out = torch.full((m, d), float("nan"), device=dev)
+            ops.gather_reduce_(csrs, xd, rsc, [None] * len(sizes), out, False)
+            names = [p[0] for p in ops.PROFILE]
+            fits = sum(sizes) * d * 4 <= 200 * 1024          # [160, 200, 100] x 512 B does not: the call falls back to the L1 / L2 kernel
+            assert ("b2g_gather_reduce_staged" in names) == (staged and fits) and ("b2g_gather_reduce" in names) == (not (staged and fits))
+            out2 = out.clone()
+            ops.gather_reduce_(csrs, xd, rsc, [None] * len(sizes), out2, True)       # accumulate
+            outs[staged] = (out, out2)
+    finally:
+        ops.GATHER_STAGED = old
+        ops.PROFILE = None
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    ref = sum((a.double() / a.sum(1).clamp(min=1).double()[:, None]) @ x.double() for a, x in zip(dense, xs))
+    assert relmax(outs[True][0], ref) < 1e-5
+    assert relmax(outs[True][1], 2 * ref) < 1e-5

@@ -4,7 +4,14 @@
 
 Every rank takes its patient partition of ONE global synthetic graph, trains 3 steps in the patient-partitioned mode
 (dist.py) and rank 0 additionally trains the same model on the whole graph on its own GPU; losses, predictions and
-parameters after the steps must agree (fp32 mode: 1e-4; only summation order differs)."""
+parameters after the steps must agree (fp32 mode: 1e-4; only summation order differs).
+
+tf32 mode: a last-bit difference of a replicated sum (BatchNorm statistics, type aggregates: different summation order on N
+ranks) can move an operand across a TF32 truncation boundary, so the two runs differ by TF32 noise, not by summation order
+only.  What is asserted there: the three losses agree to 1e-4 (observed 6e-6), the step-0 gradients agree in norm per tensor
+within the bound DESIGN section 5 states for tf32 gradients against float64 (8e-2; observed <= 6e-2 of max|grad|), parameters
+within 3 Adam steps of lr.  (The per-element "fraction off by > 1e-4" criterion of the fp32 mode is meaningless here: Adam
+normalises every gradient element to +-lr, noise included.)"""
 import importlib
 import os
 import sys
@@ -119,7 +126,7 @@ def main():
         for i in range(3):
             ref_losses.append(float(rt.train_step(rpi, rli, rev, sups[i].to(dev))))
             if i == 0:
-                rows = []
+                rows, nrows = [], []
                 for n, p in ref_model.named_parameters():
                     g0 = grads0[n]
                     if p.grad is None or g0 is None:
@@ -128,6 +135,8 @@ def main():
                         continue
                     r = p.grad[p0:p1] if n == "embeddings.patient.weight" else p.grad
                     rows.append((float((g0 - r).abs().max() / r.abs().max().clamp_min(1e-30)), n))
+                    if not (n in ("patient_transform.0.bias", "patient_transform.4.bias") or n.endswith("lin_l.bias")):   # (zero gradients)
+                        nrows.append((float((g0 - r).norm() / r.norm().clamp_min(1e-30)), n))
                 prow = []
                 for n, p in ref_model.named_parameters():
                     r = p.detach()[p0:p1] if n == "embeddings.patient.weight" else p.detach()
@@ -136,9 +145,13 @@ def main():
                 print("worst step-0 PARAM diffs after Adam:", [(round(e, 6), n, round(f, 4)) for e, n, f in prow[:10]], flush=True)
                 rows.sort(reverse=True)
                 print("worst step-0 gradient errors:", [(round(e, 5), n) for e, n in rows[:14]], flush=True)
-        tol = 1e-4 if precision == "fp32" else 5e-3
+                nrows.sort(reverse=True)
+                print("worst step-0 gradient errors in norm (tensors with a gradient):", [(round(e, 5), n) for e, n in nrows[:6]], flush=True)
+                grad_norm_err = nrows[0][0] if nrows else 0.0
+        tol = 1e-4
         for a, b in zip(losses, ref_losses):
             ok &= abs(a - b) <= tol * abs(b)
+        ok &= grad_norm_err <= (2e-4 if precision == "fp32" else 8e-2)
         worst, frac_off = 0.0, 0.0
         rsd = ref_model.state_dict()
         msd = model.state_dict()
@@ -154,9 +167,9 @@ def main():
             # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is rounding noise may move
             # the other way in the two runs (also true of two single-GPU runs with different summation order)
             frac_off = max(frac_off, float((diff > 1e-4).float().mean()))
-        ok &= worst <= 6.1e-3 and frac_off <= (0.01 if precision == "fp32" else 0.25)
+        ok &= worst <= 6.1e-3 and (frac_off <= 0.01 or precision != "fp32")
         print(f"dist_check {spec_name} world={world} precision={precision}: partitioned losses {losses} vs single-GPU {ref_losses}; "
-              f"max |param diff| after 3 Adam steps {worst:.2e} (worst per-tensor fraction of elements off by > 1e-4: {frac_off:.4f}); {n_coll} collectives in 3 steps -> {'OK' if ok else 'MISMATCH'}", flush=True)
+              f"max |param diff| after 3 Adam steps {worst:.2e} (worst per-tensor fraction of elements off by > 1e-4: {frac_off:.4f}); worst step-0 gradient error in norm {grad_norm_err:.2e}; {n_coll} collectives in 3 steps -> {'OK' if ok else 'MISMATCH'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

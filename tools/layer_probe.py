@@ -66,7 +66,7 @@ def main():
     adj = {"adjT fwd": lambda: ops.layer_adjT_tc_(x, pb.bits_out, pb, [None] * len(ys), pb.col_scale_out()),
            "adjT bwd (+dW, +db)": lambda: ops.layer_adjT_tc_(gout, pb.bits_in, pb, rs, None, with_colsum=True, dense_b=x)}
     for name, fn in adj.items():
-        for dbg in ():
+        for dbg in (0, 1, 4, 5, 7):
             os.environ["B2G_ADJT_DBG"] = str(dbg)
             print(f"{name} dbg={dbg}: {timed(fn):.4f} ms", flush=True)
     os.environ["B2G_ADJT_DBG"] = "0"
