@@ -44,7 +44,7 @@ struct TcParams {
 // dynamic smem layout (1024-byte aligned): W sub-tiles [K/32][N rows x 128 B] | X stages [2][K/32][128 rows x 128 B] |
 // epilogue staging [4 warps][32 rows x 144 B]
 // EXT & 1: BatchNorm column statistics in the epilogue; EXT & 2: row L2 normalisation in the epilogue; EXT = 0: the plain
-// kernel (separate instantiations: the statistics' accumulator registers and unrolled chunk loop cost the plain path 25 %)
+// kernel (separate instantiations: the statistics' accumulator registers cost the plain path 25 %)
 template <int EXT>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_constant__ CUtensorMap map_x,
                                                                const __grid_constant__ CUtensorMap map_w, TcParams prm) {
@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
       };
       const bool acc_staged = prm.accumulate && prm.staged;
       if (acc_staged) load_old(0, oldv);
-#pragma unroll((EXT & 1) ? 8 : 1)
-      for (int ci = 0; ci < 8; ++ci) {                     // (EXT: unrolled, the statistics accumulators are indexed by the chunk)
+#pragma unroll 1
+      for (int ci = 0; ci < 8; ++ci) {                     // (rolled: an unrolled epilogue made instruction fetch its top stall)
         const int c0 = ci * 32;
         if (c0 >= prm.n) break;
         if (acc_staged && c0 + 32 < prm.n) load_old(c0 + 32, nxtv);
@@ -221,6 +221,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (prm.bias && !(EXT & 2)) b = __ldg(reinterpret_cast<const float4*>(prm.bias + c0) + so);
         float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row0 + 32 <= prm.m) {
+          // all 32 rows live (every tile but the last): no per-row branch, so the 8 staging loads are issued back to back
+          // (a branch per row serialised load -> store -> load)
+          float4 o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = *reinterpret_cast<const float4*>(stg + (4 * j + sq) * STG_ROW + so * 16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[j].x += b.x; o[j].y += b.y; o[j].z += b.z; o[j].w += b.w;
+            if (prm.accumulate) {
+              const float4 p = oldv[j];
+              o[j].x += p.x; o[j].y += p.y; o[j].z += p.z; o[j].w += p.w;
+            }
+            *(reinterpret_cast<float4*>(prm.y + (size_t)(row0 + 4 * j + sq) * prm.n + c0) + so) = o[j];
+            if (EXT & 1) {
+              ps[0] += o[j].x; ps[1] += o[j].y; ps[2] += o[j].z; ps[3] += o[j].w;
+              pq[0] = fmaf(o[j].x, o[j].x, pq[0]); pq[1] = fmaf(o[j].y, o[j].y, pq[1]); pq[2] = fmaf(o[j].z, o[j].z, pq[2]);
+              pq[3] = fmaf(o[j].w, o[j].w, pq[3]);
+            }
+          }
+        } else
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = 4 * j + sq;
@@ -239,12 +260,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tf32(const __grid_cons
             }
           }
         }
-        if ((EXT & 1) && ci < 4) {
+        if (EXT & 1) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc_s[ci & 3][e] += ps[e];
-            acc_q[ci & 3][e] += pq[e];
-          }
+          for (int i = 0; i < 4; ++i)                        // (register arrays cannot be indexed by the loop counter: predicated adds)
+            if (ci == i) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                acc_s[i][e] += ps[e];
+                acc_q[i][e] += pq[e];
+              }
+            }
         }
         if (acc_staged) {
 #pragma unroll

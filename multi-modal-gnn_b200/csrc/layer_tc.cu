@@ -438,54 +438,51 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * prm.n);
       uint32_t rg[32];
       tmem_ld32(taddr, rg);                            // (the load of block ci + 1 is issued as soon as block ci sits in the staging tile)
-#pragma unroll
-      for (int ci = 0; ci < 8; ++ci) {
-        const int c0 = ci * 32;
-        if (c0 < prm.n) {
-          const long long t0 = tm ? clock64() : 0;
-          float4 b[8], us[8];                          // all look-ups BEFORE the staging stores: the compiler cannot tell that the two
+      // NOT unrolled: the kernel runs five different instruction streams at once and an unrolled epilogue (8 blocks x ~600
+      // instructions) made instruction fetch the epilogue's top stall (stall_no_inst), which in turn made it the critical role
+#pragma unroll 1
+      for (int c0 = 0; c0 < prm.n; c0 += 32) {
+        float4 b[8], us[8];                            // all look-ups BEFORE the staging stores: the compiler cannot tell that the two
 #pragma unroll                                         // shared-memory regions are disjoint and would serialise load -> store otherwise
-          for (int v = 0; v < 8; ++v) {                // (same address in every lane: broadcast)
-            b[v] = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * v);
-            us[v] = *reinterpret_cast<const float4*>(s_us + c0 + 4 * v);
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const long long t1 = tm ? clock64() : 0;
-          // the previous block's bulk store must have finished READING the staging tile before it is overwritten
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
-          const long long t2 = tm ? clock64() : 0;
-          if (tm) { w1 += t1 - t0; w2 += t2 - t1; }
+        for (int v = 0; v < 8; ++v) {                  // (same address in every lane: broadcast)
+          b[v] = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * v);
+          us[v] = *reinterpret_cast<const float4*>(s_us + c0 + 4 * v);
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // the previous block's bulk store must have finished READING the staging tile before it is overwritten
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            float4 o = make_float4(fmaf(__uint_as_float(rg[4 * v]), us[v].x, b[v].x), fmaf(__uint_as_float(rg[4 * v + 1]), us[v].y, b[v].y),
-                                   fmaf(__uint_as_float(rg[4 * v + 2]), us[v].z, b[v].z), fmaf(__uint_as_float(rg[4 * v + 3]), us[v].w, b[v].w));
-            if (!live) o = make_float4(0.f, 0.f, 0.f, 0.f);                               // (clipped by the store; zero for the column sums)
-            *reinterpret_cast<float4*>(stg + lane * 128 + ((v ^ (lane & 7)) << 4)) = o;
-          }
-          if (c0 + 32 < prm.n) tmem_ld32(taddr + c0 + 32, rg);
-          const long long t3 = tm ? clock64() : 0;
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          const long long t4 = tm ? clock64() : 0;
-          if (tm) { w3 += t3 - t2; w4 += t4 - t3; }
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&map_y)),
-                         "r"(smem_u32(stg)), "r"(c0), "r"((int)row0)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          if (ci < 4 && prm.stats) {
-            float sa = 0.f, sq = 0.f;                  // column c0 + lane over the warp's 32 rows (conflict-free: a row's 32 words cover all banks)
+        for (int v = 0; v < 8; ++v) {
+          float4 o = make_float4(fmaf(__uint_as_float(rg[4 * v]), us[v].x, b[v].x), fmaf(__uint_as_float(rg[4 * v + 1]), us[v].y, b[v].y),
+                                 fmaf(__uint_as_float(rg[4 * v + 2]), us[v].z, b[v].z), fmaf(__uint_as_float(rg[4 * v + 3]), us[v].w, b[v].w));
+          if (!live) o = make_float4(0.f, 0.f, 0.f, 0.f);                                 // (clipped by the store; zero for the column sums)
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((v ^ (lane & 7)) << 4)) = o;
+        }
+        if (c0 + 32 < prm.n) tmem_ld32(taddr + c0 + 32, rg);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&map_y)),
+                       "r"(smem_u32(stg)), "r"(c0), "r"((int)row0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (prm.stats) {
+          float sa = 0.f, sq = 0.f;                    // column c0 + lane over the warp's 32 rows (conflict-free: a row's 32 words cover all banks)
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const float v = *reinterpret_cast<const float*>(stg + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-              sa += v;
-              sq = fmaf(v, v, sq);
+          for (int r = 0; r < 32; ++r) {
+            const float v = *reinterpret_cast<const float*>(stg + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            sa += v;
+            sq = fmaf(v, v, sq);
+          }
+          const int ci = c0 >> 5;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)                  // (register arrays cannot be indexed by the loop counter: predicated adds)
+            if (ci == i) {
+              acc_s[i] += (double)sa;
+              acc_q[i] += (double)sq;
             }
-            acc_s[ci & 3] += (double)sa;
-            acc_q[ci & 3] += (double)sq;
-          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -522,7 +519,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
     prm.dbg_out[warp * 4 + 1] = w1;
     prm.dbg_out[warp * 4 + 2] = clock64() - t_begin;
     prm.dbg_out[warp * 4 + 3] = w2;
-    if (warp == 4) { prm.dbg_out[60] = w3; prm.dbg_out[61] = w4; }
+    if (warp == 4) { prm.dbg_out[60] = w3; prm.dbg_out[61] = w4; }      // (w1 .. w4 of the epilogue: unused since its loop is rolled)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
