@@ -535,7 +535,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
 constexpr int AT_THREADS = 512;                  // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue, 8-15 expanders
 constexpr int AT_ROWS = 32;                      // reduction rows per stage
 constexpr int AT_SUB = AT_ROWS * KB * 4;         // 4 KB sub-tile
-constexpr int AT_BSTAGES = 2;                    // ring of expanded adjacency stages (nw x 4 KB each)
+constexpr int AT_BSTAGES = 3;                    // ring of expanded adjacency stages (nw x 4 KB each): up to 3, prm.bstages in use
+constexpr int AT_NGROUPS = 2;                    // expander groups: group g expands the tiles g, g + 2, ... of the CTA
 constexpr int AT_GROUP = 4;                      // expander warps per adjacency stage: group gi = stage, warp j = words j, j+4, ...
 constexpr int AT_MAX_XSTAGES = 10;               // ring of X stages (16 KB each): deep, so that enough HBM bytes are in flight
 
@@ -550,6 +551,7 @@ struct AdjTParams {
   int dcols;                           // 128 * xb + nb
   int tmem_cols;
   int xstages;
+  int bstages;                         // adjacency stages in use (2 or 3)
   int ones;                            // 1: one more 32-column block whose first column is 1 -> column sums of X
   int dbg;                             // diagnosis only (B2G_ADJT_DBG): 1 = skip the bit expansion, 2 = skip the X loads, 4 = skip the bits loads
 };
@@ -582,7 +584,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
   if (prm.ones && warp == 3) {
     // constant block: element (row r, column 0) = 1 (32-byte chunk 0 of row r sits at chunk r & 3), everything else 0.
     // Rows beyond m contribute nothing: TMA zero-fills the matching X rows.
-    for (int sgi = 0; sgi < AT_BSTAGES; ++sgi) {
+    for (int sgi = 0; sgi < prm.bstages; ++sgi) {
       uint32_t* sub = reinterpret_cast<uint32_t*>(bbase + (size_t)sgi * b_bytes + (size_t)nw * AT_SUB);
       for (int i = lane; i < AT_SUB / 4; i += 32) {
         const int r = i >> 5, w = i & 31;
@@ -665,18 +667,21 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
         umma_commit(&bar_xempty[sx]);
         umma_commit(&bar_bempty[sb_]);
         if (++sx == nxs) { sx = 0; phx ^= 1; }
-        if (++sb_ == AT_BSTAGES) { sb_ = 0; phb ^= 1; }
+        if (++sb_ == prm.bstages) { sb_ = 0; phb ^= 1; }
       }
       umma_commit(&bar_done);
     }
   } else if (warp >= 8) {
     // expander group gi (4 warps) owns adjacency stage gi, i.e. the tiles it = gi, gi + 2, ...; inside the group warp j expands
-    // the words j, j + 4, ... of the stage's 32 rows (lane = row): two stages are being expanded at any time
+    // the words j, j + 4, ... of the stage's 32 rows (lane = row): two stages are being expanded at any time.  (A lane -> (row, half)
+    // mapping that makes the 16-byte stores bank-conflict-free -- a lane per row puts rows r and r + 4 on the same slot -- was
+    // measured 15 % SLOWER, twice: the expanders are bound by their instruction stream, not by the shared-memory pipe.)
     const int gi = (warp - 8) / AT_GROUP, j4 = (warp - 8) % AT_GROUP;
     constexpr int WPE = LY_MAXW / AT_GROUP;            // words per expander warp (6)
     uint32_t wcur[WPE], wnxt[WPE];
     float scur[LY_MAXREL], snxt[LY_MAXREL];
-    const int64_t tstep = (int64_t)gridDim.x * AT_BSTAGES;
+    const int64_t tstep = (int64_t)gridDim.x * AT_NGROUPS;
+    const int nbs = prm.bstages;
     auto load_row = [&](int64_t t, uint32_t (&w)[WPE], float (&sc)[LY_MAXREL]) {
       const int64_t row = t * AT_ROWS + lane;
       const bool live = t < n_tiles && row < prm.m && !(prm.dbg & 4);
@@ -690,11 +695,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
     };
     const int64_t t_first = blockIdx.x + (int64_t)gi * gridDim.x;
     load_row(t_first, wcur, scur);
-    uint32_t u = 0;                                    // use count of this group's stage
-    for (int64_t t = t_first; t < n_tiles; t += tstep, ++u) {
+    // tile `it` of the CTA lives in adjacency stage it % nbs (use number it / nbs of that stage).  With three stages the
+    // expansion of tile it + 2 starts when the MMAs of tile it - 1 have retired, not those of tile it: the two stages that
+    // are being expanded no longer wait for the one that is being multiplied (0.247 -> 0.224 ms at the C4 shard).
+    int it = gi;
+    for (int64_t t = t_first; t < n_tiles; t += tstep, it += AT_NGROUPS) {
       load_row(t + tstep, wnxt, snxt);
-      mbar_wait(&bar_bempty[gi], (u & 1) ^ 1);
-      uint8_t* bst = bbase + (size_t)gi * b_bytes;
+      const int sb = it % nbs;
+      mbar_wait(&bar_bempty[sb], ((uint32_t)(it / nbs) & 1u) ^ 1u);
+      uint8_t* bst = bbase + (size_t)sb * b_bytes;
 #pragma unroll
       for (int i = 0; i < WPE; ++i) {
         const int k = j4 + i * AT_GROUP;
@@ -728,7 +737,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_adjT_tf32(const __grid_consta
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_bfull[gi]);
+      if (lane == 0) mbar_arrive(&bar_bfull[sb]);
 #pragma unroll
       for (int i = 0; i < WPE; ++i) wcur[i] = wnxt[i];
 #pragma unroll
@@ -1063,16 +1072,19 @@ extern "C" int b2g_layer_fwd_tc(const float* x, const float* wcat, const uint16_
 }
 
 namespace {
-inline int adjT_xstages(int nsub, int xb) {
-  const size_t left = 224 * 1024 - (size_t)AT_BSTAGES * nsub * AT_SUB;
-  int xs = (int)(left / ((size_t)(4 + 4 * xb) * AT_SUB));
+inline int adjT_xstages(int nsub, int xb, int bstages) {
+  const long long left = 224 * 1024 - (long long)bstages * nsub * AT_SUB;
+  if (left <= 0) return 0;
+  int xs = (int)(left / ((long long)(4 + 4 * xb) * AT_SUB));
   return xs > AT_MAX_XSTAGES ? AT_MAX_XSTAGES : xs;
 }
+// three adjacency stages when at least 4 X stages (64 KB of loads in flight) still fit next to them
+inline int adjT_bstages(int nsub, int xb) { return adjT_xstages(nsub, xb, 3) >= 4 ? 3 : 2; }
 }  // namespace
 /* supported: d = 128 and 128 * with_dense + 32 * (nw + with_colsum) <= 512 TMEM columns */
 extern "C" int b2g_layer_adjT_tc_supported(int64_t m, int d, int nw) {
   if (m < 1 || d != 128 || nw < 1 || nw > 16) return 0;        // D = [128, 32 nw] fp32 must fit the 512 TMEM columns
-  return adjT_xstages(nw, 0) >= 2 ? 1 : 0;
+  return adjT_xstages(nw, 0, 2) >= 2 ? 1 : 0;
 }
 extern "C" size_t b2g_layer_adjT_tc_ws_bytes(int nw) { return (size_t)sm_count() * 128 * (128 + 32 * (size_t)nw) * 4 + 256; }
 
@@ -1107,13 +1119,18 @@ extern "C" int b2g_layer_adjT_tc(const float* x, const uint32_t* bits, const b2g
   int cols = 32;
   while (cols < prm.dcols) cols <<= 1;
   prm.tmem_cols = cols;
-  prm.xstages = adjT_xstages(nsub, prm.xb);
+  prm.bstages = adjT_bstages(nsub, prm.xb);
+  {
+    const char* eb = getenv("B2G_ADJT_BSTAGES");
+    if (eb && (atoi(eb) == 2 || (atoi(eb) == 3 && adjT_xstages(nsub, prm.xb, 3) >= 2))) prm.bstages = atoi(eb);
+  }
+  prm.xstages = adjT_xstages(nsub, prm.xb, prm.bstages);
   {
     const char* e = getenv("B2G_ADJT_DBG");
     prm.dbg = e ? atoi(e) : 0;
   }
   B2G_CHECK_ARG(prm.xstages >= 2, "layer_adjT_tc: shared memory too small for nw=%d", nw);
-  const size_t smem = (size_t)prm.xstages * (4 + 4 * prm.xb) * AT_SUB + (size_t)AT_BSTAGES * nsub * AT_SUB + 1024;
+  const size_t smem = (size_t)prm.xstages * (4 + 4 * prm.xb) * AT_SUB + (size_t)prm.bstages * nsub * AT_SUB + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     B2G_CUDA(cudaFuncSetAttribute(k_adjT_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -66,13 +66,16 @@ def main():
     adj = {"adjT fwd": lambda: ops.layer_adjT_tc_(x, pb.bits_out, pb, [None] * len(ys), pb.col_scale_out()),
            "adjT bwd (+dW, +db)": lambda: ops.layer_adjT_tc_(gout, pb.bits_in, pb, rs, None, with_colsum=True, dense_b=x)}
     for name, fn in adj.items():
-        for dbg in (0, 1, 4, 5, 7):
-            os.environ["B2G_ADJT_DBG"] = str(dbg)
-            print(f"{name} dbg={dbg}: {timed(fn):.4f} ms", flush=True)
+        for bs in (2, 3):
+            os.environ["B2G_ADJT_BSTAGES"] = str(bs)
+            for dbg in (0, 1):
+                os.environ["B2G_ADJT_DBG"] = str(dbg)
+                print(f"{name} bstages={bs} dbg={dbg}: {timed(fn):.4f} ms", flush=True)
+    os.environ.pop("B2G_ADJT_BSTAGES", None)
     os.environ["B2G_ADJT_DBG"] = "0"
     fns = {"tf32": lambda: ops.layer_fwd_tc_(x, wcat, bias, pb.bits_in, pb, rs, out),
            "f16": lambda: ops.layer_fwd_tc_(x, wcat_h, bias, pb.bits_in, pb, rs, out, None, hv)}
-    for mode, fn in fns.items():
+    for mode, fn in ():
         for dbg in (0,):
             os.environ["B2G_LAYER_DBG"] = str(dbg)
             print(f"{mode} dbg={dbg}: {timed(fn):.4f} ms", flush=True)
