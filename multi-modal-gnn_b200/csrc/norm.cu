@@ -233,34 +233,33 @@ __global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __res
 }
 
 // Element-wise passes: a thread owns 8 consecutive elements (one Philox call, two 16-byte accesses).  blockDim x 8
-// elements is a multiple of every supported d, so a thread's columns never change over the grid-stride loop; the
-// per-column constants sit in shared memory (registers are kept for loads in flight: ~40 registers -> 48 warps per SM).
-__global__ void __launch_bounds__(256, 5) k_bn_apply(const float* __restrict__ x, int64_t n8, int d, const float* __restrict__ mean,
+// elements is a multiple of every supported d, so a thread's columns never change over the grid-stride loop: the
+// per-column constants live in 32 registers (in shared memory they cost 8 LDS.128 per octet -- 4x the wavefronts of the
+// global accesses themselves: ncu showed the L1 / shared-memory pipe 91 % busy and the kernel at 4.9 TB/s); two octets
+// per trip keep four 16-byte loads in flight per thread.
+__global__ void __launch_bounds__(256, 3) k_bn_apply(const float* __restrict__ x, int64_t n8, int d, const float* __restrict__ mean,
                                                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                   int act, float p_drop, uint64_t seed, uint64_t sid, float* __restrict__ y) {
-  __shared__ __align__(16) float prm[4][256];
   if (p_drop > 0.f) resolve_seed(seed, sid);
-  for (int cc = threadIdx.x; cc < d; cc += blockDim.x) {
-    prm[0][cc] = mean[cc]; prm[1][cc] = rstd[cc]; prm[2][cc] = gamma[cc]; prm[3][cc] = beta[cc];
-  }
-  __syncthreads();
   const int c = (int)((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8) % d);
+  float mu[8], rs[8], ga[8], be[8];
+  ld8(mean + c, mu); ld8(rstd + c, rs); ld8(gamma + c, ga); ld8(beta + c, be);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    float v[8];
-    ld8(x + i * 8, v);
-    float mk[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-    if (p_drop > 0.f) dropout_scale8(seed, sid, (uint64_t)i, p_drop, mk);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += 2 * stride) {
+    float v[2][8];
+    const bool second = i + stride < n8;
+    ld8(x + i * 8, v[0]);
+    if (second) ld8(x + (i + stride) * 8, v[1]);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float4 mu = *reinterpret_cast<const float4*>(&prm[0][c + 4 * h]), rs = *reinterpret_cast<const float4*>(&prm[1][c + 4 * h]);
-      const float4 ga = *reinterpret_cast<const float4*>(&prm[2][c + 4 * h]), be = *reinterpret_cast<const float4*>(&prm[3][c + 4 * h]);
-      v[4 * h + 0] = act_fwd(fmaf((v[4 * h + 0] - mu.x) * rs.x, ga.x, be.x), act) * mk[4 * h + 0];
-      v[4 * h + 1] = act_fwd(fmaf((v[4 * h + 1] - mu.y) * rs.y, ga.y, be.y), act) * mk[4 * h + 1];
-      v[4 * h + 2] = act_fwd(fmaf((v[4 * h + 2] - mu.z) * rs.z, ga.z, be.z), act) * mk[4 * h + 2];
-      v[4 * h + 3] = act_fwd(fmaf((v[4 * h + 3] - mu.w) * rs.w, ga.w, be.w), act) * mk[4 * h + 3];
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !second) break;
+      const int64_t iu = i + u * stride;
+      float mk[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+      if (p_drop > 0.f) dropout_scale8(seed, sid, (uint64_t)iu, p_drop, mk);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[u][e] = act_fwd(fmaf((v[u][e] - mu[e]) * rs[e], ga[e], be[e]), act) * mk[e];
+      st8(y + iu * 8, v[u]);
     }
-    st8(y + i * 8, v);
   }
 }
 
