@@ -869,7 +869,7 @@ def _ptr_array(ts):
 def layer_cat_weights_(ws_list, transposed, tabs, scales, offs, kx, ktot, n, biases=()):
     """([sum of W (or its transpose) | tab_i^T * scale_i at column kx + offs[i]] -> [n, ktot],  sum of the biases or None)"""
     lib = _lib.load()
-    dev = ws_list[0].device
+    dev = ws_list[0].device if ws_list else next(t for t in tabs if t is not None).device
     out = torch.empty((n, ktot), dtype=torch.float32, device=dev)
     biases = [b for b in biases if b is not None]
     bias_out = torch.empty(n, dtype=torch.float32, device=dev) if biases else None
@@ -879,7 +879,7 @@ def layer_cat_weights_(ws_list, transposed, tabs, scales, offs, kx, ktot, n, bia
     ps = _ptr_array([sc for _, sc, _ in live] or [None])
     rows = (ctypes.c_int * max(nr, 1))(*[int(t.shape[0]) for t, _, _ in live] or [0])
     off = (ctypes.c_int * max(nr, 1))(*[int(o) for _, _, o in live] or [0])
-    _run("b2g_layer_cat_weights", lib.b2g_layer_cat_weights, _ptr_array(ws_list), len(ws_list), int(transposed),
+    _run("b2g_layer_cat_weights", lib.b2g_layer_cat_weights, _ptr_array(ws_list or [None]), len(ws_list), int(transposed),
          _ptr_array(biases or [None]), len(biases), _ptr(bias_out), n, kx, pt, ps, rows, off, nr, ktot, out.data_ptr(), _stream())
     return out, bias_out
 

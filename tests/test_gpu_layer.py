@@ -378,3 +378,37 @@ def test_gather_reduce_staged_equals_unstaged(m, sizes, density, d, pkg):
     ref = sum((a.double() / a.sum(1).clamp(min=1).double()[:, None]) @ x.double() for a, x in zip(dense, xs))
     assert relmax(outs[True][0], ref) < 1e-5
     assert relmax(outs[True][1], 2 * ref) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("half", [False, True], ids=["tf32adj", "f16adj"])
+@pytest.mark.parametrize("m,n,kx,sizes", [(1000, 64, 64, [50, 200, 100]), (3001, 256, 256, [20, 30, 25]), (20000, 128, 0, [160, 200, 100]),
+                                          (129, 32, 32, [33, 31]), (128 * 148 * 2 + 5, 128, 128, [40]), (777, 128, 128, [256, 256, 250])])
+def test_layer_fwd_tc_general_shapes(m, n, kx, sizes, half, pkg):
+    """b2g_layer_fwd_tc for every shape b2g_layer_fwd_tc_supported admits (the model only uses n = kx = 128): output widths
+    32..256, no dense part (kx = 0), one and 24 bit words per row, several tiles per CTA with a partial last tile."""
+    G, ops, _, _, L = _mods()
+    lib = L.load()
+    dev = torch.device("cuda:0")
+    dense, pb = _random_hub(G, m, sizes, [0.1] * len(sizes), dev, seed=m + n)
+    assert lib.b2g_layer_fwd_tc_supported(m, n, kx, pb.nw)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(m, max(kx, 32), generator=gen)[:, :kx].contiguous() if kx else None
+    w = torch.randn(n, max(kx, 1), generator=gen)[:, :kx].contiguous() / max(kx, 1) ** 0.5
+    b = torch.randn(n, generator=gen)
+    ys = [torch.randn(s, n, generator=gen) for s in sizes]
+    rs = [1.0 / a.sum(1).clamp(min=1) for a in dense]
+    wcat, bias = ops.layer_cat_weights_([w.to(dev)] if kx else [], False, [y.to(dev) for y in ys], [None] * len(sizes), pb.offs, kx, kx + 32 * pb.nw, n,
+                                        [b.to(dev)])
+    hv = ops.layer_cat_half_(wcat, kx) if half else None
+    out = torch.full((m, n), float("nan"), device=dev)
+    xd = x.to(dev) if kx else torch.empty((m, 0), device=dev)
+    ops.layer_fwd_tc_(xd, wcat, bias, pb.bits_in, pb, pb.rscale_in(), out, None, hv)
+    torch.cuda.synchronize()
+    ref = b.double().expand(m, n).clone()
+    if kx:
+        ref = ref + x.double() @ w.double().t()
+    for a, r, y in zip(dense, rs, ys):
+        ref += (a.double() * r.double()[:, None]) @ y.double()
+    assert torch.isfinite(out).all()
+    assert relmax(out, ref) < 3e-3
