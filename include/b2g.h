@@ -293,7 +293,7 @@ int b2g_bn_eval_stats(const float* running_mean, const float* running_var, int d
                       float* rstd, void* stream);
 /* y = dropout(act((x - mean) * rstd * gamma + beta)); `relu` is the activation code of model.py:145-153:
  * 0 none, 1 relu, 2 leaky_relu(0.01), 3 elu(1.0); dropout optional (p_drop == 0 -> none).
- * The keep mask is Philox4x32-10(seed, stream_id) per element, scaled by 1/(1-p) (F.dropout semantics). */
+ * The keep mask is Philox4x32-7(seed, stream_id) per element, scaled by 1/(1-p) (F.dropout semantics). */
 int b2g_bn_apply(const float* x, int64_t m, int d, const float* mean, const float* rstd, const float* gamma,
                  const float* beta, int relu, float p_drop, uint64_t seed, uint64_t stream_id, float* y,
                  void* stream);

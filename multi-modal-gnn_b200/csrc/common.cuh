@@ -71,7 +71,10 @@ __device__ __forceinline__ void st_stream(float4* p, float4 v) {
                "f"(v.w));
 }
 
-// Philox4x32-10 (Salmon et al. 2011) -- counter-based, so forward and backward regenerate the same mask.
+// Philox4x32-7 (Salmon et al. 2011: 7 rounds are the fewest that pass BigCrush; cuRAND's default of 10 adds margin that a
+// dropout mask does not need) -- counter-based, so forward and backward regenerate the same mask.  The decoder kernels spend
+// more than half of their instructions here (12 calls per pair).
+constexpr int PHILOX_ROUNDS = 7;
 struct Philox {
   uint32_t k0, k1;
   __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
@@ -79,7 +82,7 @@ struct Philox {
     uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
     uint32_t a = k0, b = k1;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) {
       uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
       uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
       uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
@@ -100,7 +103,7 @@ __device__ __forceinline__ void resolve_seed(uint64_t& seed, uint64_t& sid) {
   }
 }
 
-// Dropout keep-scales.  One Philox4x32-10 call yields 128 random bits = eight 16-bit uniforms; element e of dropout
+// Dropout keep-scales.  One Philox4x32-7 call yields 128 random bits = eight 16-bit uniforms; element e of dropout
 // stream `sid` uses call counter e / 8 and 16-bit lane e % 8, and is dropped when its uniform is below
 // floor(p * 65536) (keep probability quantised to 2^-16: relative error <= 1.6e-5 at p = 0.2).
 __device__ __forceinline__ void dropout_scale8(uint64_t seed, uint64_t sid, uint64_t oct, float p, float (&m)[8]) {
