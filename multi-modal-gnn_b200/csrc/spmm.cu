@@ -2,6 +2,7 @@
 // Replaces SAGEConv.propagate's index_select -> [E,d] message tensor -> scatter_add (PyG; model.py:256):
 // no message tensor is ever materialised and no floating-point atomics are used.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 using namespace b2g;
@@ -98,9 +99,92 @@ __device__ __forceinline__ void lds_row(RowVec<D>& r, const float* row, int lane
 
 // A warp owns 32 consecutive destination rows: their row pointers are one coalesced load per relation, and their column
 // indices are one contiguous stream per relation that the warp walks in 32-entry chunks held in registers (current + next
-// chunk, the next one always in flight), so no global-load latency sits between two rows; the gathered rows themselves are
-// LDS.128 from the staged tables, four in flight.  FMAs are applied in edge order, relation by relation: bit-identical to
-// k_gather_reduce.
+// chunk, the next one always in flight), so the only global-load latency left per row is that of the gathered rows
+// themselves (k_gather_reduce: row pointer -> column index -> column scale -> row, four dependent loads per row).
+// FMAs are applied in edge order, relation by relation: bit-identical to k_gather_reduce.
+// STAGED: the source tables sit in shared memory (`tab`, offsets info.off[k]) and a gathered row is an LDS.128 per lane;
+// otherwise rows come from global memory (read-only path).  MAXR: relations compiled in (their stream state lives in registers).
+template <int D, int MAXR, bool STAGED>
+__device__ __forceinline__ void gather_block32(const RelPack& rels, const StagedInfo& info, const float* tab, int n_rels, int64_t n_rows,
+                                               int64_t row0, int lane, float* __restrict__ out, int accumulate) {
+  const int nr = (int)min((int64_t)32, n_rows - row0);
+  int rp[MAXR], eblk[MAXR], base[MAXR], buf[MAXR], nxt[MAXR], cur[MAXR];
+  float rsv[MAXR], sbuf[MAXR], snxt[MAXR];
+#pragma unroll
+  for (int k = 0; k < MAXR; ++k) {
+    if (k < n_rels) {
+      const b2g_rel_t& rel = rels.r[k];
+      rp[k] = __ldg(rel.rowptr + row0 + min(lane, nr));
+      eblk[k] = __ldg(rel.rowptr + row0 + nr);
+      rsv[k] = (rel.row_scale && lane < nr) ? __ldg(rel.row_scale + row0 + lane) : 1.0f;
+      base[k] = __shfl_sync(FULL, rp[k], 0);
+      cur[k] = 0;
+      const int j0 = base[k] + lane, j1 = base[k] + 32 + lane;
+      buf[k] = j0 < eblk[k] ? __ldg(rel.col + j0) : 0;
+      nxt[k] = j1 < eblk[k] ? __ldg(rel.col + j1) : 0;
+      sbuf[k] = (rel.col_scale && j0 < eblk[k]) ? __ldg(rel.col_scale + buf[k]) : 1.0f;
+      snxt[k] = (rel.col_scale && j1 < eblk[k]) ? __ldg(rel.col_scale + nxt[k]) : 1.0f;
+    }
+  }
+  for (int r = 0; r < nr; ++r) {
+    RowVec<D> acc;
+    acc.zero();
+#pragma unroll
+    for (int k = 0; k < MAXR; ++k) {
+      if (k < n_rels) {
+        const b2g_rel_t& rel = rels.r[k];
+        const float* src = STAGED ? tab + info.off[k] : rel.x;
+        const int b = __shfl_sync(FULL, rp[k], r);
+        const int e = r + 1 < 32 ? __shfl_sync(FULL, rp[k], r + 1) : eblk[k];
+        RowVec<D> part;
+        part.zero();
+        for (int j = b; j < e; j += 4) {
+          const int idx = j - base[k];
+          while ((idx >> 5) > cur[k]) {                  // (uniform) step to the chunk of edge j; keep the one after it in flight
+            buf[k] = nxt[k];
+            sbuf[k] = snxt[k];
+            ++cur[k];
+            const int jn = base[k] + (cur[k] + 1) * 32 + lane;
+            nxt[k] = jn < eblk[k] ? __ldg(rel.col + jn) : 0;
+            snxt[k] = (rel.col_scale && jn < eblk[k]) ? __ldg(rel.col_scale + nxt[k]) : 1.0f;
+          }
+          const int cnt = min(4, e - j);
+          int c[4];
+          float sc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int id = idx + u;
+            const bool in_next = (id >> 5) > cur[k];     // uniform: a group of 4 touches at most the current and the next chunk
+            c[u] = __shfl_sync(FULL, in_next ? nxt[k] : buf[k], id & 31);
+            sc[u] = __shfl_sync(FULL, in_next ? snxt[k] : sbuf[k], id & 31);
+          }
+          RowVec<D> rw[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {                  // (a zero column scale means "row not present", as in k_gather_reduce)
+            if (u < cnt && sc[u] != 0.f) {
+              if (STAGED) lds_row<D>(rw[u], src + (size_t)c[u] * D, lane);
+              else rw[u].load(src + (size_t)c[u] * D, lane);
+            } else {
+              rw[u].zero();
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (u < cnt) part.fma(sc[u], rw[u]);
+        }
+        acc.fma(__shfl_sync(FULL, rsv[k], r), part);
+      }
+    }
+    float* o = out + (size_t)(row0 + r) * D;
+    if (accumulate) {
+      RowVec<D> prev;
+      prev.load_rw(o, lane);
+      acc.add(prev);
+    }
+    acc.store(o, lane);
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(512, 1) k_gather_reduce_staged(RelPack rels, StagedInfo info, int n_rels, int64_t n_rows,
                                                                  float* __restrict__ out, int accumulate) {
@@ -120,81 +204,18 @@ __global__ void __launch_bounds__(512, 1) k_gather_reduce_staged(RelPack rels, S
   mbar_wait(&bar, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int64_t n_blocks = (n_rows + 31) / 32;
-  for (int64_t blk = (int64_t)blockIdx.x * nwarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * nwarps) {
-    const int64_t row0 = blk * 32;
-    const int nr = (int)min((int64_t)32, n_rows - row0);
-    int rp[4], eblk[4], base[4], buf[4], nxt[4], cur[4];
-    float rsv[4], sbuf[4], snxt[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < n_rels) {
-        const b2g_rel_t& rel = rels.r[k];
-        rp[k] = __ldg(rel.rowptr + row0 + min(lane, nr));
-        eblk[k] = __ldg(rel.rowptr + row0 + nr);
-        rsv[k] = (rel.row_scale && lane < nr) ? __ldg(rel.row_scale + row0 + lane) : 1.0f;
-        base[k] = __shfl_sync(FULL, rp[k], 0);
-        cur[k] = 0;
-        const int j0 = base[k] + lane, j1 = base[k] + 32 + lane;
-        buf[k] = j0 < eblk[k] ? __ldg(rel.col + j0) : 0;
-        nxt[k] = j1 < eblk[k] ? __ldg(rel.col + j1) : 0;
-        sbuf[k] = (rel.col_scale && j0 < eblk[k]) ? __ldg(rel.col_scale + buf[k]) : 1.0f;
-        snxt[k] = (rel.col_scale && j1 < eblk[k]) ? __ldg(rel.col_scale + nxt[k]) : 1.0f;
-      }
-    }
-    for (int r = 0; r < nr; ++r) {
-      RowVec<D> acc;
-      acc.zero();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < n_rels) {
-          const b2g_rel_t& rel = rels.r[k];
-          const float* src = tab + info.off[k];
-          const int b = __shfl_sync(FULL, rp[k], r);
-          const int e = r + 1 < 32 ? __shfl_sync(FULL, rp[k], r + 1) : eblk[k];
-          RowVec<D> part;
-          part.zero();
-          for (int j = b; j < e; j += 4) {
-            const int idx = j - base[k];
-            while ((idx >> 5) > cur[k]) {                  // (uniform) step to the chunk of edge j; keep the one after it in flight
-              buf[k] = nxt[k];
-              sbuf[k] = snxt[k];
-              ++cur[k];
-              const int jn = base[k] + (cur[k] + 1) * 32 + lane;
-              nxt[k] = jn < eblk[k] ? __ldg(rel.col + jn) : 0;
-              snxt[k] = (rel.col_scale && jn < eblk[k]) ? __ldg(rel.col_scale + nxt[k]) : 1.0f;
-            }
-            const int cnt = min(4, e - j);
-            int c[4];
-            float sc[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int id = idx + u;
-              const bool in_next = (id >> 5) > cur[k];     // uniform: a group of 4 touches at most the current and the next chunk
-              c[u] = __shfl_sync(FULL, in_next ? nxt[k] : buf[k], id & 31);
-              sc[u] = __shfl_sync(FULL, in_next ? snxt[k] : sbuf[k], id & 31);
-            }
-            RowVec<D> rw[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {                  // (a zero column scale means "row not present", as in k_gather_reduce)
-              if (u < cnt && sc[u] != 0.f) lds_row<D>(rw[u], src + (size_t)c[u] * D, lane);
-              else rw[u].zero();
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (u < cnt) part.fma(sc[u], rw[u]);
-          }
-          acc.fma(__shfl_sync(FULL, rsv[k], r), part);
-        }
-      }
-      float* o = out + (size_t)(row0 + r) * D;
-      if (accumulate) {
-        RowVec<D> prev;
-        prev.load_rw(o, lane);
-        acc.add(prev);
-      }
-      acc.store(o, lane);
-    }
-  }
+  for (int64_t blk = (int64_t)blockIdx.x * nwarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * nwarps)
+    gather_block32<D, 4, true>(rels, info, tab, n_rels, n_rows, blk * 32, lane, out, accumulate);
+}
+
+// the streaming form without staging: 8 warps per CTA, a warp per 32 destination rows
+template <int D, int MAXR>
+__global__ void __launch_bounds__(256) k_gather_reduce_stream(RelPack rels, int n_rels, int64_t n_rows, float* __restrict__ out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t blk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (blk * 32 >= n_rows) return;
+  StagedInfo none{};
+  gather_block32<D, MAXR, false>(rels, none, nullptr, n_rels, n_rows, blk * 32, lane, out, accumulate);
 }
 
 template <int D>
@@ -379,8 +400,20 @@ extern "C" int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_
     B2G_CHECK_ARG(h_rels[k].rowptr && h_rels[k].x && aligned16(h_rels[k].x), "gather_reduce: relation %d has null/unaligned pointers", k);
     pack.r[k] = h_rels[k];
   }
-  unsigned grid = (unsigned)ceil_div(n_rows, 8);
-  DISPATCH_D(d, (k_gather_reduce<D><<<grid, 256, 0, st>>>(pack, n_rels, n_rows, out, accumulate)));
+  const char* es = getenv("B2G_GATHER_STREAM");              // (=0: the warp-per-row kernel at every size; tests compare the two)
+  const bool stream_off = es && atoi(es) == 0;
+  if (n_rows >= 4096 && !stream_off) {
+    // many short rows: a warp per 32 rows with the CSR streamed through registers (same arithmetic, same results)
+    unsigned grid = (unsigned)ceil_div(n_rows, 8 * 32);
+    if (n_rels == 1) {
+      DISPATCH_D(d, (k_gather_reduce_stream<D, 1><<<grid, 256, 0, st>>>(pack, n_rels, n_rows, out, accumulate)));
+    } else {
+      DISPATCH_D(d, (k_gather_reduce_stream<D, 4><<<grid, 256, 0, st>>>(pack, n_rels, n_rows, out, accumulate)));
+    }
+  } else {
+    unsigned grid = (unsigned)ceil_div(n_rows, 8);
+    DISPATCH_D(d, (k_gather_reduce<D><<<grid, 256, 0, st>>>(pack, n_rels, n_rows, out, accumulate)));
+  }
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

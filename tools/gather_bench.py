@@ -66,10 +66,11 @@ def main():
     e_in = sum(c.n_edges for c in csrs)
     nbytes = 4 * m * d + 4 * e_in + 4 * 3 * (m + 1) + 4 * m * 3 + sum(4 * x.numel() for x in xs)      # out + col + rowptr + 1/deg + tables
     res = {"workload": args.workload, "n_patient": m, "edges_in": e_in, "hbm_peak_gbs": peak, "algorithmic_bytes": nbytes}
-    for staged in (False, True):
+    for staged, stream in ((False, False), (False, True), (True, True)):
         ops.GATHER_STAGED = staged
+        os.environ["B2G_GATHER_STREAM"] = "1" if stream else "0"
         ms = timed(lambda: ops.gather_reduce_(csrs, xs, rsc, [None] * len(xs), out, False))
-        key = "b2g_gather_reduce_staged" if staged else "b2g_gather_reduce"
+        key = "b2g_gather_reduce_staged" if staged else ("b2g_gather_reduce (k_gather_reduce_stream)" if stream else "b2g_gather_reduce (k_gather_reduce, warp per row)")
         res[key] = {"ms": ms, "algorithmic_GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak, "edges_per_s": e_in / (ms * 1e-3)}
         print(key, res[key], flush=True)
     # BatchNorm statistics of a [m, 128] activation (k_col_reduce<0>): reads the array once
