@@ -385,6 +385,11 @@ int b2g_dropout_mask(int64_t n, float p_drop, uint64_t seed, uint64_t stream_id,
 int b2g_l2norm_fwd(const float* x, int64_t m, int d, float eps, float* y, float* inv_norm, void* stream);
 int b2g_l2norm_bwd(const float* y, const float* dy, const float* inv_norm, int64_t m, int d, float* dx,
                    void* stream);
+/* The same with the column sums of dx (dx_colsum[d]) from the same pass: dx is the `dy` of the nn.Linear in front of
+ * F.normalize (model.py:101-105,232), whose bias gradient is exactly this sum.  ws: b2g_l2norm_bwd_cs_ws_bytes(d). */
+size_t b2g_l2norm_bwd_cs_ws_bytes(int d);
+int b2g_l2norm_bwd_cs(const float* y, const float* dy, const float* inv_norm, int64_t m, int d, float* dx, float* dx_colsum,
+                      void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (e) fused edge decoder -- EdgeRegressionHead([64,32]) over (patient, lab) pairs, model.py:305-333,373-386

@@ -160,6 +160,8 @@ _PROTOS = {
     "b2g_dropout_mask": (c_int, [c_int64, c_float, c_uint64, c_uint64, _P, _P]),
     "b2g_l2norm_fwd": (c_int, [_P, c_int64, c_int, c_float, _P, _P, _P]),
     "b2g_l2norm_bwd": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
+    "b2g_l2norm_bwd_cs_ws_bytes": (c_size_t, [c_int]),
+    "b2g_l2norm_bwd_cs": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
     "b2g_decoder_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, c_uint64, _P, _P]),
     "b2g_decoder_fwd_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, c_uint64, _P, _P]),
     "b2g_decoder_bwd_ws_bytes": (c_size_t, [c_int64]),

@@ -456,6 +456,77 @@ __global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ y,
   gv.store(dx + (size_t)r * D, lane);
 }
 
+// The same pass with the column sums of dx riding along (dx is the `dy` of the Linear in front of the normalisation: its bias
+// gradient would otherwise cost a pass of its own).  Persistent grid; per-thread fp64 sums in row order, the CTA's 8 warps
+// combined in warp order, one record per CTA; k_rec_reduce adds the records in CTA order: deterministic.
+template <int D>
+__global__ void __launch_bounds__(256) k_l2norm_bwd_cs(const float* __restrict__ y, const float* __restrict__ dy, const float* __restrict__ inv_norm,
+                                                       int64_t m, float* __restrict__ dx, double* __restrict__ rec) {
+  __shared__ double sh[8][D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int N = RowVec<D>::N;
+  double cs[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) cs[i] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  for (int64_t r0 = (int64_t)blockIdx.x * 8 + warp; r0 < m; r0 += 2 * stride) {     // two rows per trip: four row loads in flight
+    const int64_t r1 = r0 + stride;
+    const bool two = r1 < m;
+    RowVec<D> yv[2], gv[2];
+    yv[0].load(y + (size_t)r0 * D, lane);
+    gv[0].load(dy + (size_t)r0 * D, lane);
+    if (two) {
+      yv[1].load(y + (size_t)r1 * D, lane);
+      gv[1].load(dy + (size_t)r1 * D, lane);
+    }
+    float inv[2];
+    inv[0] = __ldg(inv_norm + r0);
+    inv[1] = two ? __ldg(inv_norm + r1) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < N; ++i) dot = fmaf(yv[u].v[i], gv[u].v[i], dot);
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        gv[u].v[i] = inv[u] * (gv[u].v[i] - yv[u].v[i] * dot);
+        cs[i] += (double)gv[u].v[i];
+      }
+      gv[u].store(dx + (size_t)(u ? r1 : r0) * D, lane);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {                        // column of element i of a lane's row slice (RowVec layout)
+    const int col = D >= 128 ? (i >> 2) * 128 + lane * 4 + (i & 3) : (D == 64 ? lane * 2 + i : lane);
+    sh[warp][col] = cs[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += sh[w][c];
+    rec[(size_t)blockIdx.x * D + c] = a;
+  }
+}
+// out[c] = (float) sum over CTAs of rec[cta][c]: 8 interleaved slices of the records, combined in fixed order
+__global__ void __launch_bounds__(256) k_rec_reduce(const double* __restrict__ rec, int n_cta, int d, float* __restrict__ out) {
+  __shared__ double sh[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double a = 0.0;
+  if (c < d)
+    for (int k = slice; k < n_cta; k += 8) a += rec[(size_t)k * d + c];
+  sh[slice][lane] = a;
+  __syncthreads();
+  if (slice == 0 && c < d) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) a += sh[k][lane];
+    out[c] = (float)a;
+  }
+}
+
 // ---- loss -----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float loss_term(float diff, int kind) {
   float a = fabsf(diff);
@@ -813,6 +884,27 @@ extern "C" int b2g_l2norm_bwd(const float* y, const float* dy, const float* inv_
   B2G_CHECK_ARG(aligned16(y) && aligned16(dy) && aligned16(dx), "l2norm_bwd: unaligned pointer");
   unsigned grid = (unsigned)ceil_div(m, 8);
   DISPATCH_D(d, (k_l2norm_bwd<D><<<grid, 256, 0, (cudaStream_t)stream_>>>(y, dy, inv_norm, m, dx)));
+  B2G_LAUNCH_CHECK();
+  return B2G_OK;
+}
+
+extern "C" size_t b2g_l2norm_bwd_cs_ws_bytes(int d) { return (size_t)sm_count() * 8 * d * sizeof(double) + 256; }
+extern "C" int b2g_l2norm_bwd_cs(const float* y, const float* dy, const float* inv_norm, int64_t m, int d, float* dx, float* dx_colsum,
+                                 void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  B2G_CHECK_ARG(m > 0 && d_ok(d) && y && dy && inv_norm && dx && dx_colsum, "l2norm_bwd_cs: bad args");
+  B2G_CHECK_ARG(aligned16(y) && aligned16(dy) && aligned16(dx) && aligned16(ws), "l2norm_bwd_cs: unaligned pointer");
+  if (!ws || ws_bytes < b2g_l2norm_bwd_cs_ws_bytes(d)) {
+    set_error("l2norm_bwd_cs: workspace too small");
+    return B2G_EWS;
+  }
+  int64_t blocks = ceil_div(m, 8);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  double* rec = (double*)ws;
+  DISPATCH_D(d, (k_l2norm_bwd_cs<D><<<grid, 256, 0, st>>>(y, dy, inv_norm, m, dx, rec)));
+  B2G_LAUNCH_CHECK();
+  k_rec_reduce<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(rec, grid, d, dx_colsum);
   B2G_LAUNCH_CHECK();
   return B2G_OK;
 }

@@ -390,12 +390,19 @@ class LinearL2NormFn(Function):
         m, n = y.shape
         g = torch.empty_like(y)
         cost(12 * m * n)
-        _run("b2g_l2norm_bwd", lib.b2g_l2norm_bwd, y.data_ptr(), dy.data_ptr(), inv.data_ptr(), m, n, g.data_ptr(), _stream())
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if need_b:                          # the bias gradient (column sums of g) from the same pass
+            gsum = torch.empty(n, dtype=torch.float32, device=y.device)
+            ws = workspace(lib.b2g_l2norm_bwd_cs_ws_bytes(n), y.device)
+            _run("b2g_l2norm_bwd", lib.b2g_l2norm_bwd_cs, y.data_ptr(), dy.data_ptr(), inv.data_ptr(), m, n, g.data_ptr(), gsum.data_ptr(),
+                 ws.data_ptr(), ws.numel(), _stream())
+            _tag_colsum(g, gsum)
+        else:
+            _run("b2g_l2norm_bwd", lib.b2g_l2norm_bwd, y.data_ptr(), dy.data_ptr(), inv.data_ptr(), m, n, g.data_ptr(), _stream())
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             linear_bwd_input_(g, w, dx)
-        need_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1] or need_b:
             dw = torch.empty_like(w)
             db = torch.empty(w.shape[0], dtype=torch.float32, device=w.device) if need_b else None
