@@ -202,6 +202,17 @@ class Trainer:
         buf[0] = loss.detach()
         return self.dist.all_reduce_(buf)[0]
 
+    def _drop_unoptimized_grads(self):
+        """Graph mode only: parameters the optimizer does not hold (note N2: the lazily created tables, which the reference
+        never trains and whose .grad `optimizer.zero_grad()` never resets, so that it accumulates over all steps) start the
+        capture without a .grad -- the captured AccumulateGrad then stores the step's gradient instead of adding it to the
+        running sum (a 3-pass add over the [N_patient, d] table per step for a value nobody reads).  After a replay their
+        .grad is the LAST step's gradient, not the sum over steps; eager mode keeps the reference's behaviour."""
+        held = {id(p) for g in self.optimizer.param_groups for p in g["params"]}
+        for p in self.model.parameters():
+            if id(p) not in held:
+                p.grad = None
+
     def _capture(self, pi, li, ev, sup):
         model, dev = self.model, self.device
         model._seed_buffer = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -214,6 +225,7 @@ class Trainer:
         with torch.cuda.stream(side):                       # warm-up: allocations, caches, lazy attributes
             for _ in range(2):
                 self.optimizer.zero_grad(set_to_none=True)
+                self._drop_unoptimized_grads()
                 self._loss_of(model.predict_lab_values(self.data, pi, li), ev, li, sup_static).backward()
             if self.grad_hook is not None:                  # learn the (static) gradient pattern outside the capture
                 self._grad_pattern = gradient_pattern(self._exchanged_params(), self.dist)
@@ -223,6 +235,7 @@ class Trainer:
             for k, v in buffers.items():
                 sd[k].copy_(v)
         self.optimizer.zero_grad(set_to_none=True)
+        self._drop_unoptimized_grads()
         graph = torch.cuda.CUDAGraph()
         lib = _lib.load()
         before = int(lib.b2g_launch_count())
