@@ -108,6 +108,12 @@ typedef struct {
 int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_rows, int d, float* out,
                       int accumulate, void* stream);
 
+/* The same contraction, bit-identical results, for MANY SHORT rows (hundreds of thousands of rows with a few entries each, e.g.
+ * the per-patient reduction of the decoder's pair gradients): a warp owns 32 consecutive rows, their row pointers are one
+ * coalesced load and their column indices one stream walked in register chunks, so a row costs one dependent global load (the
+ * gathered rows) instead of four (row pointer -> column -> column scale -> row). */
+int b2g_gather_reduce_stream(const b2g_rel_t* h_rels, int n_rels, int64_t n_rows, int d, float* out, int accumulate, void* stream);
+
 /* The same contraction (identical arithmetic and edge order) with every SOURCE TABLE STAGED IN SHARED MEMORY by bulk copies
  * (cp.async.bulk + mbarrier), one resident CTA per SM: for patient destinations, whose sources are the few-hundred-row lab /
  * diagnosis / medication tables (north_star (b)).  h_n_src[k] = rows of rels[k].x; supported when they sum to <= 200 KB. */

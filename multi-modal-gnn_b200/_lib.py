@@ -99,6 +99,7 @@ _PROTOS = {
     "b2g_csr_chunk_count": (c_int, [_P, c_int64, c_int32, _P, ctypes.POINTER(c_int64), _P, c_size_t, _P]),
     "b2g_csr_chunk_fill": (c_int, [_P, c_int64, c_int32, _P, _P, _P, _P]),
     "b2g_gather_reduce": (c_int, [ctypes.POINTER(RelT), c_int, c_int64, c_int, _P, c_int, _P]),
+    "b2g_gather_reduce_stream": (c_int, [ctypes.POINTER(RelT), c_int, c_int64, c_int, _P, c_int, _P]),
     "b2g_gather_reduce_staged_supported": (c_int, [ctypes.POINTER(c_int), c_int, c_int]),
     "b2g_gather_reduce_staged": (c_int, [ctypes.POINTER(RelT), ctypes.POINTER(c_int), c_int, c_int64, c_int, _P, c_int, _P]),
     "b2g_gather_reduce_chunked": (c_int, [ctypes.POINTER(RelT), _P, _P, _P, c_int64, c_int32, c_int64, c_int, _P, c_int,

@@ -389,8 +389,8 @@ extern "C" int b2g_gather_values(const float* src, const int64_t* idx, int64_t m
   return B2G_OK;
 }
 
-extern "C" int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_rows, int d, float* out, int accumulate,
-                                 void* stream_) {
+namespace {
+int gather_reduce_impl(const b2g_rel_t* h_rels, int n_rels, int64_t n_rows, int d, float* out, int accumulate, bool stream, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   B2G_CHECK_ARG(h_rels && n_rels >= 1 && n_rels <= 4 && n_rows >= 0 && out, "gather_reduce: bad args (n_rels=%d)", n_rels);
   B2G_CHECK_ARG(aligned16(out), "gather_reduce: out not 16-byte aligned");
@@ -400,10 +400,7 @@ extern "C" int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_
     B2G_CHECK_ARG(h_rels[k].rowptr && h_rels[k].x && aligned16(h_rels[k].x), "gather_reduce: relation %d has null/unaligned pointers", k);
     pack.r[k] = h_rels[k];
   }
-  const char* es = getenv("B2G_GATHER_STREAM");              // (=0: the warp-per-row kernel at every size; tests compare the two)
-  const bool stream_off = es && atoi(es) == 0;
-  if (n_rows >= 4096 && !stream_off) {
-    // many short rows: a warp per 32 rows with the CSR streamed through registers (same arithmetic, same results)
+  if (stream) {
     unsigned grid = (unsigned)ceil_div(n_rows, 8 * 32);
     if (n_rels == 1) {
       DISPATCH_D(d, (k_gather_reduce_stream<D, 1><<<grid, 256, 0, st>>>(pack, n_rels, n_rows, out, accumulate)));
@@ -416,6 +413,16 @@ extern "C" int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_
   }
   B2G_LAUNCH_CHECK();
   return B2G_OK;
+}
+}  // namespace
+
+extern "C" int b2g_gather_reduce(const b2g_rel_t* h_rels, int n_rels, int64_t n_rows, int d, float* out, int accumulate, void* stream_) {
+  return gather_reduce_impl(h_rels, n_rels, n_rows, d, out, accumulate, false, stream_);
+}
+/* same contraction, same results: a warp per 32 destination rows with the CSR streamed through registers -- for MANY SHORT rows
+ * (hundreds of thousands of rows of a few entries: the per-patient reduction of the decoder's pair gradients) */
+extern "C" int b2g_gather_reduce_stream(const b2g_rel_t* h_rels, int n_rels, int64_t n_rows, int d, float* out, int accumulate, void* stream_) {
+  return gather_reduce_impl(h_rels, n_rels, n_rows, d, out, accumulate, true, stream_);
 }
 
 /* all source tables in shared memory: 16-byte aligned tables, sum of rows * d * 4 <= 200 KB */

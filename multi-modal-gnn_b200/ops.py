@@ -210,6 +210,12 @@ def small_colsum_group_(xs, outs):
 # the per-row dependency chain, profiles/r2_gather_bench_c4s8.json) -- opt-in with B2G_GATHER_STAGED=1
 GATHER_STAGED = os.environ.get("B2G_GATHER_STAGED", "0") == "1"
 STAGED_MIN_ROWS = 4096          # below this the one-off table copy per CTA costs more than the gathers save
+# b2g_gather_reduce_stream serialises the 32 rows of a warp: it wins when there are enough rows to fill the GPU with such warps
+# and the rows are short (C4 shard, decoder gradients by patient, 1.25 M rows x 7 entries: 0.37 -> 0.19 ms), and loses otherwise
+# (C2, 46 k rows x 75 entries: 0.04 -> 0.12 ms)
+GATHER_STREAM = os.environ.get("B2G_GATHER_STREAM", "1") != "0"
+STREAM_MIN_ROWS = 262144
+STREAM_MAX_AVG_DEG = 10
 
 
 def gather_reduce_(csrs: Sequence[CSR], xs: Sequence[torch.Tensor], row_scales, col_scales, out: torch.Tensor,
@@ -238,6 +244,9 @@ def gather_reduce_(csrs: Sequence[CSR], xs: Sequence[torch.Tensor], row_scales, 
         if GATHER_STAGED and n_rows >= STAGED_MIN_ROWS and lib.b2g_gather_reduce_staged_supported(n_src, len(grp), d):
             # few-row source tables (lab / diagnosis / medication -> patient): staged in shared memory once per CTA
             _run("b2g_gather_reduce_staged", lib.b2g_gather_reduce_staged, arr, n_src, len(grp), n_rows, d, out.data_ptr(), int(acc), _stream())
+        elif GATHER_STREAM and n_rows >= STREAM_MIN_ROWS and sum(csrs[i].n_edges for i in grp) <= STREAM_MAX_AVG_DEG * n_rows:
+            # many short rows (the per-patient reduction of the decoder's pair gradients): CSR streamed through registers
+            _run("b2g_gather_reduce", lib.b2g_gather_reduce_stream, arr, len(grp), n_rows, d, out.data_ptr(), int(acc), _stream())
         else:
             _run("b2g_gather_reduce", lib.b2g_gather_reduce, arr, len(grp), n_rows, d, out.data_ptr(), int(acc), _stream())
         acc = True

@@ -359,14 +359,14 @@ def test_gather_reduce_staged_equals_unstaged(m, sizes, density, d, pkg):
     xd = [x.to(dev) for x in xs]
     outs = {}
     old = ops.GATHER_STAGED
-    import os
     try:
         # the warp-per-row kernel (k_gather_reduce) is the reference for both streaming forms (global rows / staged tables)
-        os.environ["B2G_GATHER_STREAM"] = "0"
         ops.GATHER_STAGED = False
+        saved_stream = (ops.GATHER_STREAM, ops.STREAM_MIN_ROWS, ops.STREAM_MAX_AVG_DEG)
+        ops.GATHER_STREAM = False
         plain = torch.full((m, d), float("nan"), device=dev)
         ops.gather_reduce_(csrs, xd, rsc, [None] * len(sizes), plain, False)
-        os.environ.pop("B2G_GATHER_STREAM")
+        ops.GATHER_STREAM, ops.STREAM_MIN_ROWS, ops.STREAM_MAX_AVG_DEG = True, 1, 10 ** 9       # force the streaming form below
         for staged in (False, True):
             ops.GATHER_STAGED = staged
             ops.PROFILE = []
@@ -381,7 +381,7 @@ def test_gather_reduce_staged_equals_unstaged(m, sizes, density, d, pkg):
     finally:
         ops.GATHER_STAGED = old
         ops.PROFILE = None
-        os.environ.pop("B2G_GATHER_STREAM", None)
+        ops.GATHER_STREAM, ops.STREAM_MIN_ROWS, ops.STREAM_MAX_AVG_DEG = saved_stream
     assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
     assert torch.equal(outs[False][0], plain), "k_gather_reduce_stream differs from k_gather_reduce"
     ref = sum((a.double() / a.sum(1).clamp(min=1).double()[:, None]) @ x.double() for a, x in zip(dense, xs))

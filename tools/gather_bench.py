@@ -68,7 +68,7 @@ def main():
     res = {"workload": args.workload, "n_patient": m, "edges_in": e_in, "hbm_peak_gbs": peak, "algorithmic_bytes": nbytes}
     for staged, stream in ((False, False), (False, True), (True, True)):
         ops.GATHER_STAGED = staged
-        os.environ["B2G_GATHER_STREAM"] = "1" if stream else "0"
+        ops.GATHER_STREAM, ops.STREAM_MIN_ROWS, ops.STREAM_MAX_AVG_DEG = stream, 1, 10 ** 9
         ms = timed(lambda: ops.gather_reduce_(csrs, xs, rsc, [None] * len(xs), out, False))
         key = "b2g_gather_reduce_staged" if staged else ("b2g_gather_reduce (k_gather_reduce_stream)" if stream else "b2g_gather_reduce (k_gather_reduce, warp per row)")
         res[key] = {"ms": ms, "algorithmic_GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak, "edges_per_s": e_in / (ms * 1e-3)}

@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 python bench.py > gpurun_out/${TAG}_bench_c4s8_1gpu.json 2> gpurun_out/${TAG}_bench_c4s8_1gpu.err || exit 1
 python tools/layer_bench.py --workload C4s8 --reps 7 --out gpurun_out/${TAG}_layer_bench_c4s8.json > gpurun_out/${TAG}_layer_bench.log 2>&1 || exit 1
 python tools/gather_bench.py --out gpurun_out/${TAG}_gather_bench_c4s8.json > gpurun_out/${TAG}_gather_bench.log 2>&1 || exit 1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches_c4s8.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1800 --csv --log-file gpurun_out/${TAG}_launches_c4s8.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph > gpurun_out/${TAG}_ncu_launches.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_layer_traffic_c4s8.csv python tools/layer_bench.py --workload C4s8 --reps 1 --only-layer > gpurun_out/${TAG}_ncu_traffic.log 2>&1
