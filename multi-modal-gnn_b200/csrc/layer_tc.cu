@@ -469,20 +469,22 @@ __global__ void __launch_bounds__(LY_THREADS, 1) k_layer_tf32(const __grid_const
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (prm.stats) {
-          float sa = 0.f, sq = 0.f;                    // column c0 + lane over the warp's 32 rows (conflict-free: a row's 32 words cover all banks)
+          // column c0 + lane over the warp's 32 rows (conflict-free: a row's 32 words cover all banks); four independent
+          // partial sums each (one chain of 32 dependent adds costs 128 cycles of latency in the critical role)
+          float pa[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
             const float v = *reinterpret_cast<const float*>(stg + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-            sa += v;
-            sq = fmaf(v, v, sq);
+            pa[r & 3] += v;
+            pq[r & 3] = fmaf(v, v, pq[r & 3]);
           }
+          const double da = (double)((pa[0] + pa[1]) + (pa[2] + pa[3])), dq = (double)((pq[0] + pq[1]) + (pq[2] + pq[3]));
           const int ci = c0 >> 5;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)                  // (register arrays cannot be indexed by the loop counter: predicated adds)
-            if (ci == i) {
-              acc_s[i] += (double)sa;
-              acc_q[i] += (double)sq;
-            }
+          for (int i = 0; i < 4; ++i) {                // (register arrays cannot be indexed by the loop counter; selects, not branches:
+            acc_s[i] += (ci == i) ? da : 0.0;          //  the compiler turned predicated adds into an indirect jump)
+            acc_q[i] += (ci == i) ? dq : 0.0;
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
