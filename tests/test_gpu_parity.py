@@ -621,11 +621,13 @@ def test_tcgen05_autograd_and_training_step(dev, golden_tiny_mae, golden_c1):
     assert abs(float(loss) - blob["loss_train"]) <= 1e-3 * abs(blob["loss_train"])
     params = dict(model.named_parameters())
     # gradients pass through ~10 chained TF32 products and the cancellation inside BatchNorm's backward: the deepest
-    # ones (first MLP layer) carry the largest error; measured 6.7e-2 of max|grad| on this fixture
+    # ones (first MLP layer) carry the largest error; measured 6.7e-2 .. 7.8e-2 of max|grad| on this fixture (the CUDA path is
+    # bit-reproducible, so the bound below is a margin over a fixed number, not over noise).  The claim made for this mode is the
+    # final-metric one (tests/test_gpu_e2e_parity.py); in float64 terms the reference's own fp32 gradients are no closer.
     errs = {k_: relerr(params[k_].grad, blob["grads"][k_]) for k_ in blob["grads"]
             if not (k_ in ("patient_transform.0.bias", "patient_transform.4.bias") or k_.endswith("lin_l.bias"))}
     print("TF32 gradient errors (fraction of max|grad|):", {k_: round(v, 4) for k_, v in errs.items()})
-    assert max(errs.values()) <= 2.5e-1, errs
+    assert max(errs.values()) <= 1.2e-1, errs
 
 
 @pytest.mark.parametrize("m,n,k", [(64, 128, 128), (1000, 128, 128), (46520, 128, 128), (46521, 64, 128), (30000, 128, 64),
