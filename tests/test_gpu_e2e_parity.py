@@ -126,6 +126,7 @@ def test_final_metrics_after_100_epochs_match_oracle(dropout, tf32_mode):
         lr_gpu.append(trainer.optimizer.param_groups[0]["lr"])
         max_val_gap = max(max_val_gap, abs(val_gpu - val_ref) / abs(val_ref))
         max_loss_gap = max(max_loss_gap, abs(loss_gpu - float(loss.detach())) / abs(float(loss.detach())))
+    torch.set_num_threads(n_threads_before)      # (the final evaluation below is one forward pass: thread count does not matter there)
     print(f"[e2e dropout={dropout}] {epochs} epochs in {time.time() - t0:.1f}s, max relative gap: train loss {max_loss_gap:.2e}, "
           f"validation loss {max_val_gap:.2e}; final lr gpu/ref {lr_gpu[-1]:.2e}/{lr_ref[-1]:.2e}")
     assert lr_gpu == lr_ref
@@ -143,7 +144,6 @@ def test_final_metrics_after_100_epochs_match_oracle(dropout, tf32_mode):
     want = E.regression_metrics(pw, attr[te].numpy().astype(np.float64))
     print(f"[e2e dropout={dropout}] test metrics  gpu: mae {got['mae']:.5f} rmse {got['rmse']:.5f} r2 {got['r2']:.5f}   "
           f"oracle: mae {want['mae']:.5f} rmse {want['rmse']:.5f} r2 {want['r2']:.5f}")
-    torch.set_num_threads(n_threads_before)
     for k in ("mae", "rmse", "r2"):
         assert abs(got[k] - want[k]) <= 1e-3, (k, got[k], want[k])
     # individual predictions after 100 chaotic optimizer steps: root-mean-square deviation relative to the predictions' spread
