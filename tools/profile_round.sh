@@ -17,4 +17,12 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_l
     python tools/layer_bench.py --workload C4s8 --reps 1 --only-layer > gpurun_out/${TAG}_ncu_full_layer.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_gather_reduce|k_col_reduce|k_bn_apply" -c 12 -f \
     -o gpurun_out/${TAG}_ncu_gather_bn_kernels python tools/gather_bench.py --reps 1 > gpurun_out/${TAG}_ncu_full_gather.log 2>&1
+# condense the reports on the box: gpurun copies gpurun_out/ back only while it stays under 64 MiB, and a full-set report of a few
+# dozen launches is 20-100 MB (a 101 MB report of the step's top kernels was lost that way this round)
+for rep in gpurun_out/${TAG}_ncu_layer_kernels gpurun_out/${TAG}_ncu_gather_bn_kernels; do
+  if [ -f ${rep}.ncu-rep ]; then
+    python tools/ncu_summary.py ${rep}.ncu-rep > ${rep}_summary.csv
+    if [ $(du -sm gpurun_out | cut -f1) -gt 56 ]; then rm -f ${rep}.ncu-rep; fi
+  fi
+done
 ls -la gpurun_out | grep ${TAG}
