@@ -12,10 +12,13 @@
 //   k_adjT_tf32    T[types, 128] = (diag(s) A)^T . x_p                          (forward: neighbour sums onto the type nodes;
 //                                 backward: dY = (diag(1/deg_p) A)^T . dout_p)
 //
-// Both expand the bits into TF32 operand tiles in shared memory with dedicated "expander" warps (generic-proxy stores in the
+// Both expand the bits into operand tiles in shared memory with dedicated "expander" warps (generic-proxy stores in the
 // tensor core's swizzled layout + fence.proxy.async), so the adjacency costs 4 bytes per 32 potential edges of HBM traffic.
-// HBM traffic per patient row: forward 512 B (x_p) + 512 B (out_p) + bits; the reduction operands (W_root | Y, 128 x K fp32)
-// stream from L2 one 32-column chunk at a time next to the matching A chunk.
+// k_layer_tf32 expands into fp16 {0 | 1/deg} tiles by default and multiplies them with kind::f16 MMAs into the accumulator
+// that the kind::tf32 MMAs of the x part feed (b2g_layer_cat_half supplies the fp16 Y rows, a power-of-two scale per output
+// column); k_adjT_tf32 expands into TF32 tiles (its other operand, X, is fp32 straight from TMA).
+// HBM traffic per patient row: forward 512 B (x_p) + 512 B (out_p) + bits; the reduction operands (W_root | Y) stream from
+// L2 one chunk at a time next to the matching A chunk.
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
